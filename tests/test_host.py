@@ -1,0 +1,138 @@
+"""CPU tests of the host logic and of the C-ABI surface (no compute calls without a GPU)."""
+import os
+import re
+import wave
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    from voicefixer_b200 import _lib
+    hdr = open(os.path.join(ROOT, "include", "vfx_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(vfx_[a-z_0-9]+)\s*\(", hdr))
+    assert declared, "no declarations parsed"
+    lib = _lib.load()
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in include/vfx_b200.h but not exported"
+    assert declared == set(_lib.SIGNATURES), "ctypes signatures out of sync with the header"
+    assert lib.vfx_version() >= 100
+
+
+def test_conv_desc_layout_matches_header():
+    """ctypes mirror of struct vfx_conv_desc has the same field order as the header."""
+    from voicefixer_b200 import _lib
+    hdr = open(os.path.join(ROOT, "include", "vfx_b200.h")).read()
+    body = re.search(r"typedef struct vfx_conv_desc \{(.*?)\} vfx_conv_desc;", hdr, flags=re.S).group(1)
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    names = []
+    for stmt in body.split(";"):
+        stmt = stmt.strip()
+        if not stmt:
+            continue
+        decl = re.sub(r"^(const\s+)?(void|float|int|long long)\s*\*?", "", stmt).strip()
+        for part in decl.split(","):
+            names.append(re.sub(r"\[.*\]", "", part).replace("*", "").strip())
+    assert names == [f[0] for f in _lib.ConvDesc._fields_]
+
+
+def test_engine_refuses_without_gpu():
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from voicefixer_b200.engine import Engine
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        Engine({}, {})
+
+
+def test_weight_packing_shapes(states):
+    from voicefixer_b200 import weights
+    from voicefixer_b200.engine import Engine
+    pa = weights.pack_analysis(states[0], "fp32")
+    pv = weights.pack_vocoder(states[1], "bf16")
+    assert tuple(pa["unet.enc1.b1.conv1.w"].shape) == (9, 32, 2)
+    assert tuple(pa["unet.dec1.up.w"].shape) == (9, 384, 384)
+    assert tuple(pa["dn.g7.l0.whh_t"].shape) == (2, 256, 768)
+    assert tuple(pv["voc.up0.w"].shape) == (14, 512, 1024) and pv["voc.up0.w"].dtype == torch.bfloat16
+    assert tuple(pv["voc.rs3.l7.c2.w"].shape) == (3, 64, 64)
+    assert tuple(pv["voc.post.w"].shape) == (7, 64) and pv["voc.post.w"].dtype == torch.float32
+    # mel filterbank band table covers every non-zero
+    fbT = pa["fe.fbT"]
+    for m in (0, 1, 64, 127):
+        s, n = int(pa["fe.fb_start"][m]), int(pa["fe.fb_len"][m])
+        mask = torch.zeros(1025, dtype=torch.bool); mask[s:s + n] = True
+        assert torch.all(fbT[m][~mask] == 0)
+    table, total = Engine.layout({**pa, **pv})
+    assert all(off % 256 == 0 for _, off, _ in table) and total > 3e8
+    # weight-norm fold and both key layouts agree
+    from voicefixer_b200 import synthetic
+    old = synthetic.make_vocoder_state(1, old_style_keys=True)
+    pv2 = weights.pack_vocoder(old, "fp32")
+    pv1 = weights.pack_vocoder(states[1], "fp32")
+    assert torch.equal(pv1["voc.rs0.l3.c1.w"], pv2["voc.rs0.l3.c1.w"])
+    w = pv1["voc.up2.w"]        # ConvTranspose1d: norm over dims (1,2) per IN channel == g
+    g = states[1]["generator.9.layer.parametrizations.weight.original0"].reshape(-1)
+    assert torch.allclose(w.permute(2, 1, 0).pow(2).sum((1, 2)).sqrt(), g, rtol=1e-4)
+
+
+def test_stft_kernel_check_rejects_foreign_window(states):
+    from voicefixer_b200 import weights
+    bad = dict(states[0])
+    bad["f_helper.stft.conv_real.weight"] = torch.ones(1025, 1, 2048)
+    with pytest.raises(ValueError, match="Hann"):
+        weights.check_stft_kernels(bad)
+
+
+def test_missing_checkpoints_raise_reference_errors(tmp_path, monkeypatch):
+    monkeypatch.setenv("HOME", str(tmp_path))
+    from voicefixer_b200 import api
+    with pytest.raises(RuntimeError, match="Error 1"):
+        api.VoiceFixer()
+    with pytest.raises(RuntimeError, match="Error 1"):
+        api.Vocoder(44100)
+    with pytest.raises(RuntimeError, match="only support 44100"):
+        api.Vocoder(16000)
+    os.makedirs(tmp_path / ".cache/voicefixer/synthesis_module/44100")
+    torch.save({"generator": {}}, tmp_path / api.VOCODER_CKPT)
+    with pytest.raises(RuntimeError, match="Error 0"):
+        api.VoiceFixer()
+
+
+def test_wav_io_roundtrip_and_int16_truncation(tmp_path):
+    from voicefixer_b200 import wavio
+    x = np.array([[0.0, 0.5, -0.5, 0.99997, -1.0, 1.5 / 32768, -1.5 / 32768]], dtype=np.float32)
+    p = tmp_path / "a.wav"
+    wavio.save_wave(x, str(p), 44100)
+    with wave.open(str(p), "rb") as f:
+        assert f.getnchannels() == 1 and f.getframerate() == 44100 and f.getsampwidth() == 2
+        pcm = np.frombuffer(f.readframes(f.getnframes()), dtype="<i2")
+    assert pcm.tolist() == [0, 16384, -16384, 32767, -32768, 1, -1]      # astype(np.short): toward zero
+    y = wavio.load_mono(str(p), 44100)
+    assert y.dtype == np.float32 and y.shape == (7,) and abs(y[1] - 0.5) < 1e-4
+    with pytest.raises(RuntimeError, match="FLAC"):
+        wavio.load_mono("x.flac")
+
+
+def test_segmentation_matches_reference_loop():
+    """The while-loop at voicefixer/base.py:117-137 cuts [0,30s), [30s,60s), ... + ragged tail."""
+    from voicefixer_b200.api import SEG_LENGTH
+    for n in (1, SEG_LENGTH - 1, SEG_LENGTH, SEG_LENGTH + 1, 3 * SEG_LENGTH + 5):
+        segs, bp = [], SEG_LENGTH
+        while bp < n + SEG_LENGTH:
+            segs.append((max(bp - SEG_LENGTH, 0), min(bp, n)))
+            bp += SEG_LENGTH
+        assert segs[0][0] == 0 and segs[-1][1] == n
+        assert all(a[1] == b[0] for a, b in zip(segs, segs[1:]))
+        assert len(segs) == (n + SEG_LENGTH - 1) // SEG_LENGTH
+
+
+def test_oracle_conditions_match_oracle_module():
+    from voicefixer_b200.api import oracle_conditions
+    from oracle import vf_oracle as O
+    wav = (np.random.RandomState(5).randn(9000) * 0.1).astype(np.float32)
+    a = oracle_conditions(wav)                                  # (1, Tc, 128) channels-last
+    b = O.oracle_cond(wav).numpy()                              # (1, 128, Tc)
+    assert a.shape == (1, b.shape[2], 128)
+    assert np.max(np.abs(a - b.transpose(0, 2, 1))) < 1e-4

@@ -1,0 +1,194 @@
+"""Drop-in mirror of the reference's public API (voicefixer/base.py, voicefixer/vocoder/base.py).
+
+Same class names, method signatures, checkpoint paths and error types; the bodies run the
+hand-written sm_100a kernels through the C-ABI engine.  The `cuda` argument is accepted for
+signature compatibility: the computation always runs on the GPU (there is no CPU path)."""
+import os
+import numpy as np
+import torch
+
+from .engine import Engine, default_precision
+from . import wavio
+
+SEG_LENGTH = 44100 * 30                      # voicefixer/base.py:116
+ANALYSIS_CKPT = ".cache/voicefixer/analysis_module/checkpoints/vf.ckpt"
+VOCODER_CKPT = ".cache/voicefixer/synthesis_module/44100/model.ckpt-1490000_trimed.pt"
+
+_ERR0 = ("Error 0: The checkpoint for analysis module (vf.ckpt) is not found in "
+         "~/.cache/voicefixer/analysis_module/checkpoints.")
+_ERR1 = ("Error 1: The checkpoint for synthesis module / vocoder (model.ckpt-1490000_trimed) is not found in "
+         "~/.cache/voicefixer/synthesis_module/44100.")
+
+
+def _check_cuda(cuda):
+    # tools/pytorch_util.py:6-8
+    if not torch.cuda.is_available():
+        if cuda:
+            raise RuntimeError("Error: You set cuda=True but no cuda device found.")
+        raise RuntimeError("voicefixer_b200 has no CPU path: a B200 (sm_100a) device is required.")
+
+
+def _load_vocoder_state():
+    path = os.path.join(os.path.expanduser("~"), VOCODER_CKPT)
+    if not os.path.exists(path):
+        raise RuntimeError(_ERR1)
+    return torch.load(path, map_location="cpu")["generator"]
+
+
+class _ModelShim:
+    """Stands in for `VoiceFixer._model` (the reference nn.Module): callers poke
+    `.parameters()`, `.to()`, `.eval()`, `.train()` and `.vocoder` (test/streamlit.py:40-42)."""
+
+    def __init__(self, owner):
+        self._owner = owner
+        self.vocoder = owner._vocoder
+
+    def parameters(self):
+        return iter([self._owner._engine.arena])
+
+    def to(self, *a, **k):
+        return self
+
+    def eval(self):
+        return self
+
+    def train(self, mode=True):
+        return self
+
+
+class Vocoder:
+    """voicefixer/vocoder/base.py:10-77."""
+
+    def __init__(self, sample_rate, _engine=None, precision=None):
+        if sample_rate != 44100:           # vocoder/config.py:28-31
+            raise RuntimeError("Error: Vocoder currently only support 44100 samplerate.")
+        self.rate = sample_rate
+        if _engine is None:
+            voc = _load_vocoder_state()
+            _check_cuda(False)
+            from .weights import pack_vocoder
+            _engine = Engine(packed=pack_vocoder(voc, precision or default_precision()), precision=precision)
+            self._standalone = True
+        self._engine = _engine
+
+    def forward(self, mel, cuda=False):
+        """non-normalised mel [B, 1, T, 128] -> [B, 1, (T + T%2 + 4)*441] (vocoder/base.py:42-56)."""
+        assert mel.size()[-1] == 128
+        _check_cuda(cuda)
+        out = self._engine.vocoder(mel[:, 0], input_is_log=False)
+        out = out[:, None, :]
+        return out if cuda else out.cpu()
+
+    __call__ = forward
+
+    def oracle(self, fpath, out_path, cuda=False):
+        """vocoder/base.py:58-77: wav file -> |STFT| -> Slaney mel -> normalise -> Generator -> file."""
+        _check_cuda(cuda)
+        wav = wavio.read_wave(fpath, self.rate)[..., 0]
+        cond = oracle_conditions(wav)
+        out = self._engine.vocoder_cond(torch.from_numpy(cond), scale=2.0 ** 15)
+        wavio.save_wave(out[:, None, :].cpu().numpy(), out_path, sample_rate=self.rate)
+
+
+def oracle_conditions(wav):
+    """Host front end of Vocoder.oracle (vocoder/base.py:61-73; numpy in the reference too):
+    peak-normalise, |STFT| (2048/441/Hann/center, librosa-0.10 zero padding), Slaney-normalised
+    HTK mel (librosa.filters.mel defaults), dB - 20, normalise, pad -> (1, Tc, 128) channels-last."""
+    wav = np.asarray(wav, dtype=np.float32)
+    wav = wav / np.max(np.abs(wav))
+    n_fft, hop = 2048, 441
+    win = (0.5 - 0.5 * np.cos(2 * np.pi * np.arange(n_fft) / n_fft)).astype(np.float32)
+    x = np.pad(wav, (n_fft // 2, n_fft // 2), mode="constant")
+    nfr = 1 + (len(x) - n_fft) // hop
+    idx = np.arange(n_fft)[None, :] + hop * np.arange(nfr)[:, None]
+    stft = np.abs(np.fft.rfft(x[idx] * win[None, :], axis=1).astype(np.complex64))      # (T, 1025)
+    mel = stft @ wavio.slaney_htk_mel_basis().T                                         # (T, 128)
+    min_level = np.exp(-100 / 20 * np.log(10))
+    S = 20 * np.log10(np.maximum(min_level, np.abs(mel))) - 20
+    S = np.clip(8.0 * ((S + 115.0) / 115.0) - 4.0, -4.0, 4.0).astype(np.float32)
+    pad_tail = S.shape[0] % 2 + 4
+    return np.concatenate([S, np.full((pad_tail, 128), -4.0, np.float32)], 0)[None]
+
+
+class VoiceFixer:
+    """voicefixer/base.py:10-146."""
+
+    def __init__(self, precision=None):
+        self.analysis_module_ckpt = os.path.join(os.path.expanduser("~"), ANALYSIS_CKPT)
+        voc = _load_vocoder_state()        # the reference builds Vocoder first (restorer/model.py:180)
+        if not os.path.exists(self.analysis_module_ckpt):
+            raise RuntimeError(_ERR0)
+        ana = torch.load(self.analysis_module_ckpt, map_location="cpu")
+        _check_cuda(False)
+        self._engine = Engine(ana, voc, precision=precision)
+        self._vocoder = Vocoder(44100, _engine=self._engine)
+        self._model = _ModelShim(self)
+
+    # -- helpers kept from the reference API
+    def _load_wav(self, path, sample_rate, threshold=0.95):
+        return wavio.load_mono(path, sample_rate)                       # base.py:47-49
+
+    def _trim_center(self, est, ref):                                   # base.py:63-76
+        diff = abs(est.shape[-1] - ref.shape[-1])
+        if est.shape[-1] == ref.shape[-1]:
+            return est, ref
+        if est.shape[-1] > ref.shape[-1]:
+            min_len = min(est.shape[-1], ref.shape[-1])
+            est = est[..., int(diff // 2): -int(diff // 2)]
+            return est[..., :min_len], ref[..., :min_len]
+        min_len = min(est.shape[-1], ref.shape[-1])
+        ref = ref[..., int(diff // 2): -int(diff // 2)]
+        return est[..., :min_len], ref[..., :min_len]
+
+    def remove_higher_frequency(self, wav, ratio=0.95):                 # base.py:87-104
+        out, _ = self._engine.hf_cut(torch.from_numpy(np.ascontiguousarray(wav, dtype=np.float32))[None], ratio)
+        return out[0].cpu().numpy()
+
+    @torch.no_grad()
+    def restore_inmem(self, wav_10k, cuda=False, mode=0, your_vocoder_func=None, drop_masks_fn=None):
+        """np (L,) float32 -> np (1, L) float32 (base.py:106-139).  The 30 s segments are
+        independent, so all full segments run as one batch and the ragged tail as a
+        second one; results are concatenated in order."""
+        _check_cuda(cuda)
+        if mode not in (0, 1, 2):
+            raise ValueError("mode must be 0, 1 or 2")
+        wav = np.ascontiguousarray(wav_10k, dtype=np.float32)
+        n = wav.shape[0]
+        segs = []
+        bp = SEG_LENGTH
+        while bp < n + SEG_LENGTH:                                       # base.py:117-119
+            segs.append(wav[bp - SEG_LENGTH: bp])
+            bp += SEG_LENGTH
+        eng = self._engine
+        dev = f"cuda:{eng.device}"
+        res = []
+        groups = {}
+        for i, s in enumerate(segs):
+            groups.setdefault(len(s), []).append(i)
+        outs = [None] * len(segs)
+        for L, idxs in groups.items():
+            x = torch.from_numpy(np.stack([segs[i] for i in idxs])).to(dev)
+            if mode == 1:
+                x, _ = eng.hf_cut(x)                                     # shorter: 512*(L//512)
+            masks = drop_masks_fn(x.shape[0], 1 + x.shape[1] // 441) if (mode == 2 and drop_masks_fn) else None
+            if your_vocoder_func is None:
+                y = eng.restore(x, mode=2 if mode == 2 else 0, drop_masks=masks)
+            else:                                                        # base.py:126-129
+                mel = eng.frontend(x)
+                mel_log = eng.analysis(mel, mode=2 if mode == 2 else 0, drop_masks=masks)
+                denoised = (10 ** torch.clip(mel_log, max=5))[:, None]
+                y = your_vocoder_func(denoised)
+                y = torch.as_tensor(y).to(dev).float()
+                if torch.max(torch.abs(y)) > 1.0:                        # base.py:131-133
+                    y = y / torch.max(torch.abs(y))
+                    print("Warning: Exceed energy limit,", "input")
+                y, _ = self._trim_center(y[:, 0], x)
+            for k, i in enumerate(idxs):
+                outs[i] = y[k]
+        out = torch.cat(outs, -1)[None]
+        return out.cpu().numpy()
+
+    def restore(self, input, output, cuda=False, mode=0, your_vocoder_func=None):
+        wav_10k = self._load_wav(input, sample_rate=44100)               # base.py:141-146
+        out_np_wav = self.restore_inmem(wav_10k, cuda=cuda, mode=mode, your_vocoder_func=your_vocoder_func)
+        wavio.save_wave(out_np_wav, fname=output, sample_rate=44100)

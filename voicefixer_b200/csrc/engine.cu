@@ -1,0 +1,722 @@
+// vfx_b200 engine: weight registry, workspace planning and the launch sequence of the restore()
+// hot path behind the C ABI of include/vfx_b200.h.  One engine per process/GPU; all device memory
+// (weights, workspace, inputs, outputs) is owned by the caller; only two small constant tables
+// (Hann window, FFT twiddles) are allocated here at create time.
+#include <math.h>
+#include <stdarg.h>
+#include <string.h>
+#include <mutex>
+#include <unordered_map>
+#include <vector>
+#include "vfx_common.cuh"
+
+namespace vfx {
+
+static thread_local char g_err[1024] = "";
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+struct Tensor { const void* p; size_t bytes; };
+
+}  // namespace vfx
+
+struct vfx_engine {
+  int device = 0;
+  int precision = VFX_PREC_FP32;
+  bool finalized = false;
+  int use_tc = 1;   // BF16: tcgen05 kernel where the shape allows (0 = SIMT bf16 cross-check)
+  std::unordered_map<std::string, vfx::Tensor> tensors;
+  float* d_window = nullptr;    // periodic Hann, 2048
+  float2* d_tw = nullptr;       // exp(-2 pi i k / 2048), k < 1024
+  std::vector<std::string> missing;
+  size_t esz() const { return precision == VFX_PREC_BF16 ? 2 : 4; }
+};
+
+namespace vfx {
+
+namespace {
+
+constexpr int UNET_C[7] = {2, 32, 64, 128, 256, 384, 384};       // channels per level (0 = input)
+constexpr int VOC_CIN[4] = {1024, 512, 256, 128};
+constexpr int VOC_COUT[4] = {512, 256, 128, 64};
+constexpr int VOC_U[4] = {7, 7, 3, 3};
+
+// ------------------------------------------------------------------ workspace bump allocator
+struct Bump {
+  char* base; size_t cap; size_t off = 0; size_t peak = 0; bool overflow = false;
+  Bump(void* b, size_t c) : base((char*)b), cap(c) {}
+  void* raw(size_t bytes) {
+    off = (off + 255) & ~(size_t)255;
+    size_t o = off;
+    off += bytes;
+    if (off > peak) peak = off;
+    if (base == nullptr) return (void*)(uintptr_t)(256 + o);   // dry run: fake non-null pointer
+    if (off > cap) { overflow = true; return base; }
+    return base + o;
+  }
+  template <typename T> T* alloc(size_t n) { return (T*)raw(n * sizeof(T)); }
+  size_t mark() const { return off; }
+  void reset(size_t m) { off = m; }
+};
+
+struct Ctx {
+  vfx_engine* e; cudaStream_t st; Bump* ws; bool dry; int mode; int rc = VFX_OK;
+  bool train() const { return mode == VFX_MODE_TRAIN_BN; }
+  int prec() const { return e->precision; }
+};
+
+#define VFX_TRY(expr) do { int _r = (expr); if (_r != VFX_OK) return _r; } while (0)
+
+const void* get(Ctx& c, const std::string& name, size_t bytes) {
+  auto it = c.e->tensors.find(name);
+  if (it == c.e->tensors.end()) {
+    c.e->missing.push_back(name);
+    set_error("weight tensor '%s' not registered", name.c_str());
+    c.rc = VFX_ERR_MISSING_WEIGHT;
+    return nullptr;
+  }
+  if (it->second.bytes != bytes) {
+    set_error("weight tensor '%s' has %zu bytes, engine expects %zu", name.c_str(), it->second.bytes, bytes);
+    c.rc = VFX_ERR_INVALID;
+    return nullptr;
+  }
+  return it->second.p;
+}
+const float* getf(Ctx& c, const std::string& name, size_t n) { return (const float*)get(c, name, n * 4); }
+const void* getw(Ctx& c, const std::string& name, size_t n, int prec) {
+  return get(c, name, n * (prec == VFX_PREC_BF16 ? 2 : 4));
+}
+
+int run_conv(Ctx& c, int prec, const vfx_conv_desc& d) {
+  if (c.dry) return VFX_OK;
+  if (c.rc != VFX_OK) return c.rc;
+  if (prec == VFX_PREC_BF16 && c.e->use_tc) {
+    int r = conv_gemm_tc(d, c.st);
+    if (r != VFX_ERR_UNSUPPORTED) return r;
+  }
+  return conv_gemm_simt(prec, d, c.st);
+}
+
+vfx_conv_desc conv_base(const void* a, int B, int H, int W, int Cin, const void* w, int N) {
+  vfx_conv_desc d;
+  memset(&d, 0, sizeof(d));
+  d.a = a; d.B = B; d.H = H; d.W = W; d.Cin = Cin;
+  d.a_sW = Cin; d.a_sH = (long long)W * Cin; d.a_sB = (long long)H * W * Cin;
+  d.w = w; d.N = N; d.Hq = H; d.Wq = W; d.sh = 1; d.sw = 1; d.OH = H; d.OW = W;
+  d.bias_mod = N;
+  return d;
+}
+void set_raw(vfx_conv_desc& d, float* p, long long ld, int col) {
+  d.out_raw = p; d.o_sW = ld; d.o_sH = (long long)d.OW * ld; d.o_sB = (long long)d.OH * d.OW * ld; d.o_col = col;
+}
+void set_act(vfx_conv_desc& d, void* p, long long ld, int col, int act, float param) {
+  d.out_act = p; d.oa_sW = ld; d.oa_sH = (long long)d.OW * ld; d.oa_sB = (long long)d.OH * d.OW * ld;
+  d.oa_col = col; d.act = act; d.act_param = param;
+}
+void set_res(vfx_conv_desc& d, const float* p, long long ld, int col) {
+  d.residual = p; d.r_sW = ld; d.r_sH = (long long)d.OW * ld; d.r_sB = (long long)d.OH * d.OW * ld; d.r_col = col;
+}
+void taps3x3(vfx_conv_desc& d, long long mat) {
+  d.ntaps = 9;
+  for (int kh = 0; kh < 3; ++kh)
+    for (int kw = 0; kw < 3; ++kw) {
+      int t = kh * 3 + kw;
+      d.dh[t] = kh - 1; d.dw[t] = kw - 1; d.w_off[t] = (long long)t * mat;
+    }
+}
+
+// ------------------------------------------------------------------ BN handling
+struct BnRef { const float* scale; const float* shift; int stat_sB; };
+
+// Eval: the folded running-stat affine registered by the host ("<name>.scale/.shift").
+// Train (mode 2): per-item biased batch statistics of `x`.
+int bn_resolve(Ctx& c, const std::string& name, int bn_C, const float* x, long long x_sB, long long ldx,
+               int B, long long P, int C, BnRef* out) {
+  if (!c.train()) {
+    out->scale = getf(c, name + ".scale", bn_C);
+    out->shift = getf(c, name + ".shift", bn_C);
+    out->stat_sB = 0;
+    return c.rc;
+  }
+  const float* gamma = getf(c, name + ".gamma", bn_C);
+  const float* beta = getf(c, name + ".beta", bn_C);
+  float* sc = c.ws->alloc<float>((size_t)B * bn_C);
+  float* sh = c.ws->alloc<float>((size_t)B * bn_C);
+  double* acc = c.ws->alloc<double>((size_t)2 * B * bn_C);
+  out->scale = sc; out->shift = sh; out->stat_sB = bn_C;
+  if (c.dry || c.rc != VFX_OK) return c.rc;
+  return bn_stats(x, x_sB, ldx, B, P, C, bn_C, gamma, beta, sc, sh, acc, c.st);
+}
+
+// operand = act(bn(x)); x raw fp32 [B][P][C] (pitch ldx) -> dense operand [B][P][C]
+int bn_act_op(Ctx& c, int prec, const std::string& bn, int bn_C, const float* x, long long x_sB,
+              long long ldx, int B, long long P, int C, int act, float slope, void* y) {
+  BnRef r;
+  VFX_TRY(bn_resolve(c, bn, bn_C, x, x_sB, ldx, B, P, C, &r));
+  if (c.dry) return VFX_OK;
+  return bn_act(prec, x, x_sB, ldx, B, P, C, r.scale, r.shift, bn_C, r.stat_sB, act, slope, y,
+                (long long)P * C, C, c.st);
+}
+
+// ------------------------------------------------------------------ UNet
+// ConvBlockRes.forward voicefixer/restorer/modules.py:68-76 on a channels-last raw tensor.
+// in: raw fp32 [B][H][W][Cin] with pitch ld_in; out: raw fp32 with pitch ld_out (+col), may alias in.
+struct BlockScratch { void* opA; float* rawH; void* opH; float* rawS; void* opX; };
+
+int conv_block(Ctx& c, const std::string& p, const float* in, long long ld_in, int B, int H, int W,
+               int Cin, int Cout, float* out, long long ld_out, const BlockScratch& s) {
+  const int prec = c.prec();
+  const long long P = (long long)H * W;
+  VFX_TRY(bn_act_op(c, prec, p + ".bn1", Cin, in, P * ld_in, ld_in, B, P, Cin, VFX_ACT_LRELU, 0.01f, s.opA));
+  {
+    vfx_conv_desc d = conv_base(s.opA, B, H, W, Cin, getw(c, p + ".conv1.w", (size_t)9 * Cout * Cin, prec), Cout);
+    taps3x3(d, (long long)Cout * Cin);
+    set_raw(d, s.rawH, Cout, 0);
+    VFX_TRY(run_conv(c, prec, d));
+  }
+  VFX_TRY(bn_act_op(c, prec, p + ".bn2", Cout, s.rawH, P * Cout, Cout, B, P, Cout, VFX_ACT_LRELU, 0.01f, s.opH));
+  const float* res = in; long long ld_res = ld_in;
+  if (Cin != Cout) {
+    const void* xin = in;
+    if (prec != VFX_PREC_FP32 || ld_in != Cin) {   // shortcut consumes raw x as a dense operand
+      if (!c.dry) VFX_TRY(bn_act(prec, in, P * ld_in, ld_in, B, P, Cin, nullptr, nullptr, Cin, 0, VFX_ACT_NONE, 0.f,
+                                 s.opX, P * Cin, Cin, c.st));
+      xin = s.opX;
+    }
+    vfx_conv_desc d = conv_base(xin, B, H, W, Cin, getw(c, p + ".sc.w", (size_t)Cout * Cin, prec), Cout);
+    d.ntaps = 1;
+    d.bias = getf(c, p + ".sc.b", Cout);
+    set_raw(d, s.rawS, Cout, 0);
+    VFX_TRY(run_conv(c, prec, d));
+    res = s.rawS; ld_res = Cout;
+  }
+  {
+    vfx_conv_desc d = conv_base(s.opH, B, H, W, Cout, getw(c, p + ".conv2.w", (size_t)9 * Cout * Cout, prec), Cout);
+    taps3x3(d, (long long)Cout * Cout);
+    set_res(d, res, ld_res, 0);
+    set_raw(d, out, ld_out, 0);
+    VFX_TRY(run_conv(c, prec, d));
+  }
+  return c.rc;
+}
+
+// UNetResComplex_100Mb.forward voicefixer/restorer/model_kqq_bn.py:130-181.
+// unet_in raw [B][Tp][127][2]; returns pointer to the last feature map raw [B][Tp][127][32].
+int unet_forward(Ctx& c, const float* unet_in, int B, int Tp, float** feat_out) {
+  const int prec = c.prec();
+  int Hl[7], Wl[7];
+  Hl[0] = Tp; Wl[0] = 127;                       // level l (1..6) works at Hl[l-1] x Wl[l-1]
+  for (int l = 1; l < 7; ++l) { Hl[l] = Hl[l - 1] / 2; Wl[l] = Wl[l - 1] / 2; }
+  const size_t esz = c.e->esz();
+  const size_t P1 = (size_t)B * Tp * 127;
+  BlockScratch s;
+  s.opA = c.ws->raw(P1 * 64 * esz);
+  s.rawH = c.ws->alloc<float>(P1 * 32);
+  s.opH = c.ws->raw(P1 * 32 * esz);
+  s.rawS = c.ws->alloc<float>(P1 * 32);
+  s.opX = c.ws->raw(P1 * 64 * esz);
+  float* cat[7]; float* pool[7];
+  for (int l = 1; l <= 6; ++l) {
+    const size_t P = (size_t)B * Hl[l - 1] * Wl[l - 1];
+    cat[l] = c.ws->alloc<float>(P * 2 * UNET_C[l]);
+    pool[l] = c.ws->alloc<float>((size_t)B * Hl[l] * Wl[l] * UNET_C[l]);
+  }
+  char name[96];
+  // ---- encoder: level l output lives in the second half of the decoder's concat buffer
+  const float* x = unet_in; int Cx = 2;
+  for (int l = 1; l <= 6; ++l) {
+    const int H = Hl[l - 1], W = Wl[l - 1], C = UNET_C[l];
+    float* skip = cat[l] + C;                     // pitch 2C
+    for (int j = 1; j <= 4; ++j) {
+      snprintf(name, sizeof(name), "unet.enc%d.b%d", l, j);
+      if (j == 1) VFX_TRY(conv_block(c, name, x, Cx, B, H, W, Cx, C, skip, 2 * C, s));
+      else VFX_TRY(conv_block(c, name, skip, 2 * C, B, H, W, C, C, skip, 2 * C, s));
+    }
+    if (!c.dry) VFX_TRY(avgpool2x2(skip, (long long)H * W * 2 * C, (long long)W * 2 * C, 2 * C, B, H, W, C, pool[l], c.st));
+    x = pool[l]; Cx = C;
+  }
+  // ---- centre block (in place on pool[6]): conv_block7
+  VFX_TRY(conv_block(c, "unet.center", pool[6], 384, B, Hl[6], Wl[6], 384, 384, pool[6], 384, s));
+  float* xd = pool[6];
+  int Cd = 384;
+  // ---- decoder i = 1..6 at level l = 7 - i  (DecoderBlockRes.forward restorer/modules.py:149-157)
+  for (int i = 1; i <= 6; ++i) {
+    const int l = 7 - i;
+    const int H = Hl[l], W = Wl[l];               // input grid
+    const int OH = Hl[l - 1], OW = Wl[l - 1];     // output grid (= 2H, 2W+1)
+    const int Cout = UNET_C[l];
+    snprintf(name, sizeof(name), "unet.dec%d", i);
+    const std::string p(name);
+    const long long Pin = (long long)H * W;
+    VFX_TRY(bn_act_op(c, prec, p + ".bn1", Cd, xd, Pin * Cd, Cd, B, Pin, Cd, VFX_ACT_LRELU, 0.0f, s.opA));
+    const void* wt = getw(c, p + ".up.w", (size_t)9 * Cout * Cd, prec);
+    for (int rh = 0; rh < 2; ++rh)
+      for (int rw = 0; rw < 2; ++rw) {
+        vfx_conv_desc d = conv_base(s.opA, B, H, W, Cd, wt, Cout);
+        d.Hq = H; d.Wq = W + 1; d.sh = 2; d.sw = 2; d.rh = rh; d.rw = rw; d.OH = OH; d.OW = OW;
+        int n = 0;
+        for (int kh = (rh ? 1 : 0); kh < 3; kh += 2)
+          for (int kw = (rw ? 1 : 0); kw < 3; kw += 2) {
+            d.dh[n] = kh == 2 ? -1 : 0; d.dw[n] = kw == 2 ? -1 : 0;
+            d.w_off[n] = (long long)(kh * 3 + kw) * Cout * Cd;
+            ++n;
+          }
+        d.ntaps = n;
+        set_raw(d, cat[l], 2 * Cout, 0);
+        VFX_TRY(run_conv(c, prec, d));
+      }
+    // conv_block2..5: first consumes the concat tensor (2C -> C, with shortcut)
+    float* dl = pool[l];                          // dense [B][OH][OW][Cout]: reuse? sizes differ -> own buffer
+    dl = c.ws->alloc<float>((size_t)B * OH * OW * Cout);
+    for (int j = 2; j <= 5; ++j) {
+      snprintf(name, sizeof(name), "unet.dec%d.b%d", i, j);
+      if (j == 2) VFX_TRY(conv_block(c, name, cat[l], 2 * Cout, B, OH, OW, 2 * Cout, Cout, dl, Cout, s));
+      else VFX_TRY(conv_block(c, name, dl, Cout, B, OH, OW, Cout, Cout, dl, Cout, s));
+    }
+    xd = dl; Cd = Cout;
+  }
+  VFX_TRY(conv_block(c, "unet.after", xd, 32, B, Tp, 127, 32, 32, xd, 32, s));
+  *feat_out = xd;
+  return c.rc;
+}
+
+// ------------------------------------------------------------------ denoiser
+// nn.Sequential voicefixer/restorer/model.py:69-99 (always fp32 SIMT: 1 % of the path's FLOPs,
+// recurrent part is precision-sensitive).  mel [B][T][128] -> lin15 raw [B*T][128].
+int linear(Ctx& c, const void* a, long long M, int K, const std::string& p, int N, float* out_raw,
+           void* out_act, int act) {
+  vfx_conv_desc d = conv_base(a, 1, 1, (int)M, K, getf(c, p + ".w", (size_t)N * K), N);
+  d.ntaps = 1;
+  d.bias = getf(c, p + ".b", N);
+  if (out_raw) set_raw(d, out_raw, N, 0);
+  if (out_act) set_act(d, out_act, N, 0, act, 0.f);
+  if (c.dry) return c.rc;
+  if (c.rc != VFX_OK) return c.rc;
+  return conv_gemm_simt(VFX_PREC_FP32, d, c.st);
+}
+
+int bn_gru(Ctx& c, const std::string& p, const float* x, int B, int T, float* op, float* gi,
+           float* y0, float* y1) {
+  const long long M = (long long)B * T;
+  // BN2d(1) over the (T,512) plane of each item
+  VFX_TRY(bn_act_op(c, VFX_PREC_FP32, p + ".bn", 1, x, (long long)T * 512, 512, B, T, 512, VFX_ACT_NONE, 0.f, op));
+  const float* in = op;
+  float* outs[2] = {y0, y1};
+  for (int layer = 0; layer < 2; ++layer) {
+    char nm[64];
+    snprintf(nm, sizeof(nm), "%s.l%d", p.c_str(), layer);
+    const std::string q(nm);
+    vfx_conv_desc d = conv_base(in, 1, 1, (int)M, 512, getf(c, q + ".wih", (size_t)1536 * 512), 1536);
+    d.ntaps = 1;
+    d.bias = getf(c, q + ".bih", 1536);
+    set_raw(d, gi, 1536, 0);
+    const float* whh = getf(c, q + ".whh_t", (size_t)2 * 256 * 768);
+    const float* bhh = getf(c, q + ".bhh", 2 * 768);
+    if (!c.dry && c.rc == VFX_OK) {
+      VFX_TRY(conv_gemm_simt(VFX_PREC_FP32, d, c.st));
+      VFX_TRY(gru_layer(gi, whh, bhh, B, T, outs[layer], c.st));
+    }
+    in = outs[layer];
+  }
+  return c.rc;
+}
+
+int denoiser_forward(Ctx& c, const float* mel, int B, int T, const uint8_t* drop, float* lin_out) {
+  const long long M = (long long)B * T;
+  float* a = c.ws->alloc<float>(M * 512);
+  float* b = c.ws->alloc<float>(M * 512);
+  float* y0 = c.ws->alloc<float>(M * 512);
+  float* gi = c.ws->alloc<float>(M * 1536);
+  const std::string p = "dn.";
+  VFX_TRY(bn_act_op(c, VFX_PREC_FP32, p + "bn0", 1, mel, (long long)T * 128, 128, B, T, 128, VFX_ACT_NONE, 0.f, a));
+  VFX_TRY(linear(c, a, M, 128, p + "lin1", 256, nullptr, b, VFX_ACT_LRELU));         // ReLU (slope 0)
+  VFX_TRY(bn_act_op(c, VFX_PREC_FP32, p + "bn3", 1, b, (long long)T * 256, 256, B, T, 256, VFX_ACT_NONE, 0.f, a));
+  VFX_TRY(linear(c, a, M, 256, p + "lin4", 512, b, nullptr, 0));
+  if (c.train() && drop && !c.dry) VFX_TRY(dropout_apply(b, drop, M * 512, c.st));
+  if (!c.dry) VFX_TRY(bn_act(VFX_PREC_FP32, b, (long long)T * 512, 512, B, T, 512, nullptr, nullptr, 1, 0, VFX_ACT_LRELU,
+                             0.f, b, (long long)T * 512, 512, c.st));                   // ReLU in place
+  VFX_TRY(bn_gru(c, p + "g7", b, B, T, a, gi, y0, b));       // result in b
+  VFX_TRY(bn_gru(c, p + "g8", b, B, T, a, gi, y0, b));
+  VFX_TRY(bn_act_op(c, VFX_PREC_FP32, p + "bn9", 1, b, (long long)T * 512, 512, B, T, 512, VFX_ACT_LRELU, 0.f, a));
+  VFX_TRY(linear(c, a, M, 512, p + "lin11", 512, b, nullptr, 0));
+  if (c.train() && drop && !c.dry) VFX_TRY(dropout_apply(b, drop + M * 512, M * 512, c.st));
+  VFX_TRY(bn_act_op(c, VFX_PREC_FP32, p + "bn13", 1, b, (long long)T * 512, 512, B, T, 512, VFX_ACT_LRELU, 0.f, a));
+  VFX_TRY(linear(c, a, M, 512, p + "lin15", 128, lin_out, nullptr, 0));
+  return c.rc;
+}
+
+int analysis_forward(Ctx& c, const float* mel, int B, int T, const uint8_t* drop, float* mel_log_out) {
+  const int Tp = (T + 63) / 64 * 64;
+  const size_t m0 = c.ws->mark();
+  float* xlog = c.ws->alloc<float>((size_t)B * T * 128);
+  float* unet_in = c.ws->alloc<float>((size_t)B * Tp * 127 * 2);
+  float* lin = c.ws->alloc<float>((size_t)B * T * 128);
+  {
+    const size_t m1 = c.ws->mark();
+    VFX_TRY(denoiser_forward(c, mel, B, T, drop, lin));
+    c.ws->reset(m1);
+  }
+  if (!c.dry) VFX_TRY(mask_log_pack(lin, mel, B, T, Tp, xlog, unet_in, c.st));
+  float* feat = nullptr;
+  VFX_TRY(unet_forward(c, unet_in, B, Tp, &feat));
+  const float* hw = getf(c, "unet.head.w", 32);
+  const float* hb = getf(c, "unet.head.b", 1);
+  if (!c.dry && c.rc == VFX_OK) VFX_TRY(unet_head(feat, B, T, Tp, hw, hb, xlog, mel_log_out, c.st));
+  c.ws->reset(m0);
+  return c.rc;
+}
+
+// ------------------------------------------------------------------ vocoder
+// vocoder Generator.forward voicefixer/vocoder/model/generator.py:127-145 on cond [B][Tc][128]
+// (operand precision), then the fused post conv / tanh / trim.
+int vocoder_generator(Ctx& c, const void* cond, int B, int Tc, float* wav_out, int trim_len, float scale) {
+  const int prec = c.prec();
+  const size_t esz = c.e->esz();
+  const size_t m0 = c.ws->mark();
+  const long long S = (long long)Tc * 441;
+  // condnet buffers
+  void* c0 = c.ws->raw((size_t)B * (Tc + 6) * 512 * esz);
+  void* c1 = c.ws->raw((size_t)B * (Tc + 6) * 512 * esz);
+  // full-rate buffers: X raw fp32, A0 / Hh / U operands
+  const size_t maxel = (size_t)B * S * 64;
+  float* X = c.ws->alloc<float>(maxel);
+  void* A0 = c.ws->raw(maxel * esz);
+  void* Hh = c.ws->raw(maxel * esz);
+  void* U = c.ws->raw(maxel * esz);
+  char name[96];
+  // ---- condnet: 5 x (Conv1d k3 p1 + ELU), generator.py:33-54
+  const void* in = cond; int Cin = 128;
+  void* pp[2] = {c0, c1};
+  for (int i = 0; i < 5; ++i) {
+    snprintf(name, sizeof(name), "voc.cond%d", i);
+    const std::string p(name);
+    vfx_conv_desc d = conv_base(in, B, 1, Tc, Cin, getw(c, p + ".w", (size_t)3 * 512 * Cin, prec), 512);
+    d.ntaps = 3;
+    for (int k = 0; k < 3; ++k) { d.dw[k] = k - 1; d.w_off[k] = (long long)k * 512 * Cin; }
+    d.bias = getf(c, p + ".b", 512);
+    void* out = pp[i & 1];
+    if (i == 4) {   // last ELU output goes to rows 3..Tc+2 of the reflect-padded buffer
+      set_act(d, (char*)out + (size_t)3 * 512 * esz, 512, 0, VFX_ACT_ELU, 0.f);
+      d.oa_sB = (long long)(Tc + 6) * 512;
+    } else {
+      set_act(d, out, 512, 0, VFX_ACT_ELU, 0.f);
+    }
+    VFX_TRY(run_conv(c, prec, d));
+    in = out; Cin = 512;
+  }
+  if (!c.dry) VFX_TRY(reflect_pad3((void*)in, B, Tc, 512, prec, c.st));
+  // ---- ReflectionPad1d(3) + Conv1d(512,1024,k7) + LeakyReLU(0.2); the x + sin x of the first
+  //      UpsampleNet (modules.py:504) is applied in the same epilogue.
+  {
+    vfx_conv_desc d = conv_base(in, B, 1, Tc + 6, 512, getw(c, "voc.pre.w", (size_t)7 * 1024 * 512, prec), 1024);
+    d.ntaps = 7; d.Wq = Tc; d.OW = Tc;
+    for (int k = 0; k < 7; ++k) { d.dw[k] = k; d.w_off[k] = (long long)k * 1024 * 512; }
+    d.bias = getf(c, "voc.pre.b", 1024);
+    set_act(d, U, 1024, 0, VFX_ACT_LRELU_XSINX, 0.2f);
+    VFX_TRY(run_conv(c, prec, d));
+  }
+  long long Lin = Tc;
+  for (int j = 0; j < 4; ++j) {
+    const int Ci = VOC_CIN[j], Co = VOC_COUT[j], u = VOC_U[j];
+    const long long Lout = Lin * u;
+    // ---- UpsampleNet: ConvTranspose1d(k=2u, s=u, p, op) as two phase-group GEMMs (modules.py:451-459)
+    snprintf(name, sizeof(name), "voc.up%d", j);
+    {
+      const std::string p(name);
+      const void* w = getw(c, p + ".w", (size_t)2 * u * Co * Ci, prec);
+      const float* bias = getf(c, p + ".b", Co);
+      const int pad = u / 2 + u % 2, nA = u - pad;
+      const long long mat = (long long)Co * Ci;
+      for (int grp = 0; grp < 2; ++grp) {
+        const int nph = grp == 0 ? nA : u - nA;
+        vfx_conv_desc d = conv_base(U, B, 1, (int)Lin, Ci, w, nph * Co);
+        d.ntaps = 2;
+        if (grp == 0) { d.dw[0] = 0; d.w_off[0] = pad * mat; d.dw[1] = -1; d.w_off[1] = (pad + u) * mat; d.rw = 0; }
+        else          { d.dw[0] = 1; d.w_off[0] = 0;         d.dw[1] = 0;  d.w_off[1] = u * mat;         d.rw = nA; }
+        d.sw = u; d.OW = (int)Lout;
+        d.bias = bias; d.bias_mod = Co;
+        set_raw(d, X, Co, 0);
+        set_act(d, A0, Co, 0, VFX_ACT_LRELU, 0.01f);
+        VFX_TRY(run_conv(c, prec, d));
+      }
+    }
+    // ---- ResStack: 8 x (x + conv_k3_d1(lrelu(conv_k3_d3^i(lrelu(x))))), modules.py:550-576,592-595
+    int dil = 1;
+    for (int i = 0; i < 8; ++i, dil *= 3) {
+      snprintf(name, sizeof(name), "voc.rs%d.l%d", j, i);
+      const std::string p(name);
+      {
+        vfx_conv_desc d = conv_base(A0, B, 1, (int)Lout, Co, getw(c, p + ".c1.w", (size_t)3 * Co * Co, prec), Co);
+        d.ntaps = 3;
+        for (int k = 0; k < 3; ++k) { d.dw[k] = (k - 1) * dil; d.w_off[k] = (long long)k * Co * Co; }
+        d.bias = getf(c, p + ".c1.b", Co);
+        set_act(d, Hh, Co, 0, VFX_ACT_LRELU, 0.01f);
+        VFX_TRY(run_conv(c, prec, d));
+      }
+      {
+        vfx_conv_desc d = conv_base(Hh, B, 1, (int)Lout, Co, getw(c, p + ".c2.w", (size_t)3 * Co * Co, prec), Co);
+        d.ntaps = 3;
+        for (int k = 0; k < 3; ++k) { d.dw[k] = k - 1; d.w_off[k] = (long long)k * Co * Co; }
+        d.bias = getf(c, p + ".c2.b", Co);
+        set_res(d, X, Co, 0);
+        set_raw(d, X, Co, 0);
+        if (i < 7) set_act(d, A0, Co, 0, VFX_ACT_LRELU, 0.01f);
+        else if (j < 3) set_act(d, U, Co, 0, VFX_ACT_LRELU_XSINX, 0.2f);   // act + next UpsampleNet's x+sin x
+        VFX_TRY(run_conv(c, prec, d));
+      }
+    }
+    Lin = Lout;
+  }
+  // ---- LeakyReLU(0.2) + ReflectionPad1d(3) + Conv1d(64,1,7) + Tanh + _trim_center
+  int lo = 0; long long out_len = S;
+  if (trim_len >= 0) {
+    VFX_REQUIRE(trim_len <= S, "vocoder: trim_len %d exceeds generated length %lld", trim_len, S);
+    const long long diff = S - trim_len;
+    lo = (int)(diff / 2); out_len = trim_len;
+    VFX_REQUIRE(diff == 0 || diff / 2 >= 1, "vocoder: _trim_center is degenerate for a length difference of 1");
+  }
+  const float* pw = getf(c, "voc.post.w", 7 * 64);
+  const float* pb = getf(c, "voc.post.b", 1);
+  if (!c.dry && c.rc == VFX_OK) VFX_TRY(voc_post(X, B, (int)S, pw, pb, lo, (int)out_len, scale, wav_out, c.st));
+  c.ws->reset(m0);
+  return c.rc;
+}
+
+int vocoder_forward(Ctx& c, const float* mel, int B, int T, int input_is_log, float* wav_out, int trim_len,
+                    float scale) {
+  const int Tc = T + T % 2 + 4;
+  const size_t m0 = c.ws->mark();
+  void* cond = c.ws->raw((size_t)B * Tc * 128 * c.e->esz());
+  const float* tab = getf(c, "voc.mel_tab", 129);
+  if (!c.dry && c.rc == VFX_OK) VFX_TRY(voc_normalize(mel, B, T, Tc, input_is_log, tab, cond, c.prec(), c.st));
+  VFX_TRY(vocoder_generator(c, cond, B, Tc, wav_out, trim_len, scale));
+  c.ws->reset(m0);
+  return c.rc;
+}
+
+int frontend_forward(Ctx& c, const float* wav, int B, int L, float* mel, float* sp) {
+  const int T = 1 + L / 441;
+  const float* fbT = getf(c, "fe.fbT", (size_t)128 * 1025);
+  const int* fs = (const int*)get(c, "fe.fb_start", 128 * 4);
+  const int* fl = (const int*)get(c, "fe.fb_len", 128 * 4);
+  if (c.dry || c.rc != VFX_OK) return c.rc;
+  return stft_mel(wav, B, L, T, c.e->d_window, c.e->d_tw, fbT, fs, fl, mel, sp, c.st);
+}
+
+int restore_forward(Ctx& c, const float* wav, int B, int L, const uint8_t* drop, float* wav_out) {
+  const int T = 1 + L / 441;
+  float* mel = c.ws->alloc<float>((size_t)B * T * 128);
+  float* mel_log = c.ws->alloc<float>((size_t)B * T * 128);
+  VFX_TRY(frontend_forward(c, wav, B, L, mel, nullptr));
+  VFX_TRY(analysis_forward(c, mel, B, T, drop, mel_log));
+  VFX_TRY(vocoder_forward(c, mel_log, B, T, 1, wav_out, L, 1.0f));
+  return c.rc;
+}
+
+}  // namespace
+}  // namespace vfx
+
+// ====================================================================== C ABI
+using namespace vfx;
+
+extern "C" {
+
+const char* vfx_last_error(void) { return vfx::g_err; }
+int vfx_version(void) { return 100; }
+
+int vfx_engine_create(vfx_engine** out, int device, int precision) {
+  VFX_REQUIRE(out != nullptr, "engine_create: out is null");
+  VFX_REQUIRE(precision == VFX_PREC_FP32 || precision == VFX_PREC_BF16, "engine_create: bad precision %d", precision);
+  int ndev = 0;
+  VFX_CUDA_CHECK(cudaGetDeviceCount(&ndev));
+  VFX_REQUIRE(device >= 0 && device < ndev, "engine_create: device %d not present (%d devices)", device, ndev);
+  VFX_CUDA_CHECK(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  VFX_CUDA_CHECK(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10) {
+    set_error("vfx_b200 is built for sm_100a only; device %d is sm_%d%d", device, prop.major, prop.minor);
+    return VFX_ERR_UNSUPPORTED;
+  }
+  vfx_engine* e = new vfx_engine();
+  e->device = device; e->precision = precision;
+  std::vector<float> win(2048);
+  std::vector<float2> tw(1024);
+  for (int n = 0; n < 2048; ++n) win[n] = (float)(0.5 - 0.5 * cos(2.0 * M_PI * n / 2048.0));
+  for (int k = 0; k < 1024; ++k) {
+    tw[k].x = (float)cos(-2.0 * M_PI * k / 2048.0);
+    tw[k].y = (float)sin(-2.0 * M_PI * k / 2048.0);
+  }
+  VFX_CUDA_CHECK(cudaMalloc(&e->d_window, 2048 * sizeof(float)));
+  VFX_CUDA_CHECK(cudaMalloc(&e->d_tw, 1024 * sizeof(float2)));
+  VFX_CUDA_CHECK(cudaMemcpy(e->d_window, win.data(), 2048 * sizeof(float), cudaMemcpyHostToDevice));
+  VFX_CUDA_CHECK(cudaMemcpy(e->d_tw, tw.data(), 1024 * sizeof(float2), cudaMemcpyHostToDevice));
+  *out = e;
+  return VFX_OK;
+}
+
+int vfx_engine_destroy(vfx_engine* e) {
+  if (!e) return VFX_OK;
+  cudaFree(e->d_window);
+  cudaFree(e->d_tw);
+  delete e;
+  return VFX_OK;
+}
+
+int vfx_engine_set_option(vfx_engine* e, const char* key, int value) {
+  VFX_REQUIRE(e && key, "set_option: null argument");
+  if (!strcmp(key, "use_tc")) { e->use_tc = value; return VFX_OK; }
+  set_error("set_option: unknown key '%s'", key);
+  return VFX_ERR_INVALID;
+}
+
+int vfx_engine_set_tensor(vfx_engine* e, const char* name, const void* dev_ptr, size_t bytes) {
+  VFX_REQUIRE(e && name && dev_ptr, "set_tensor: null argument");
+  e->tensors[name] = vfx::Tensor{dev_ptr, bytes};
+  e->finalized = false;
+  return VFX_OK;
+}
+
+static int dry_run(vfx_engine* e, int B, int T, int L, size_t* bytes) {
+  Bump ws(nullptr, 0);
+  Ctx c{e, nullptr, &ws, true, VFX_MODE_TRAIN_BN};
+  int r;
+  if (L > 0) r = restore_forward(c, nullptr, B, L, nullptr, nullptr);
+  else {
+    float* mel = ws.alloc<float>((size_t)B * T * 128);
+    r = analysis_forward(c, mel, B, T, nullptr, mel);
+    if (r == VFX_OK) r = vocoder_forward(c, mel, B, T, 1, nullptr, -1, 1.f);
+  }
+  *bytes = ws.peak + 4096;
+  return r;
+}
+
+int vfx_engine_finalize(vfx_engine* e) {
+  VFX_REQUIRE(e, "finalize: null engine");
+  e->missing.clear();
+  size_t bytes = 0;
+  int r = dry_run(e, 1, 64, 0, &bytes);
+  {   // also the front-end tables
+    Bump ws(nullptr, 0);
+    Ctx c{e, nullptr, &ws, true, VFX_MODE_EVAL};
+    int r2 = frontend_forward(c, nullptr, 1, 44100, nullptr, nullptr);
+    if (r == VFX_OK) r = r2;
+  }
+  if (!e->missing.empty()) {
+    std::string s = "missing weight tensors:";
+    for (size_t i = 0; i < e->missing.size() && i < 12; ++i) s += " " + e->missing[i];
+    if (e->missing.size() > 12) s += " ...";
+    set_error("%s (%zu total)", s.c_str(), e->missing.size());
+    return VFX_ERR_MISSING_WEIGHT;
+  }
+  if (r != VFX_OK) return r;
+  e->finalized = true;
+  return VFX_OK;
+}
+
+size_t vfx_workspace_bytes(const vfx_engine* e, int B, int L) {
+  if (!e || B <= 0 || L <= 1024) return 0;
+  size_t bytes = 0;
+  dry_run(const_cast<vfx_engine*>(e), B, 0, L, &bytes);
+  return bytes;
+}
+
+size_t vfx_workspace_bytes_frames(const vfx_engine* e, int B, int T) {
+  if (!e || B <= 0 || T <= 0) return 0;
+  size_t bytes = 0;
+  dry_run(const_cast<vfx_engine*>(e), B, T, 0, &bytes);
+  return bytes;
+}
+
+#define VFX_ENTER(e)                                                                     \
+  VFX_REQUIRE((e) != nullptr, "null engine");                                            \
+  VFX_REQUIRE((e)->finalized, "engine not finalized (call vfx_engine_finalize)");        \
+  VFX_CUDA_CHECK(cudaSetDevice((e)->device))
+
+#define VFX_FINISH(c, ws)                                                                \
+  if ((ws).overflow) { set_error("workspace too small: need %zu bytes", (ws).peak); return VFX_ERR_WORKSPACE; } \
+  return (c).rc
+
+int vfx_frontend_mel(vfx_engine* e, const float* wav, int B, int L, float* mel, float* sp_out, void* stream) {
+  VFX_ENTER(e);
+  VFX_REQUIRE(wav && mel && B > 0, "frontend: bad arguments");
+  Bump ws(nullptr, 0);
+  Ctx c{e, (cudaStream_t)stream, &ws, false, VFX_MODE_EVAL};
+  return frontend_forward(c, wav, B, L, mel, sp_out);
+}
+
+int vfx_analysis(vfx_engine* e, const float* mel, int B, int T, int mode, const uint8_t* drop_masks,
+                 float* mel_log_out, void* workspace, size_t workspace_bytes, void* stream) {
+  VFX_ENTER(e);
+  VFX_REQUIRE(mel && mel_log_out && B > 0 && T > 0 && workspace, "analysis: bad arguments");
+  VFX_REQUIRE(mode == VFX_MODE_EVAL || mode == VFX_MODE_TRAIN_BN, "analysis: bad mode %d", mode);
+  Bump ws(workspace, workspace_bytes);
+  Ctx c{e, (cudaStream_t)stream, &ws, false, mode};
+  int r = analysis_forward(c, mel, B, T, drop_masks, mel_log_out);
+  if (r != VFX_OK) return r;
+  VFX_FINISH(c, ws);
+}
+
+int vfx_vocoder(vfx_engine* e, const float* mel, int B, int T, int input_is_log, float* wav_out, int trim_len,
+                float scale, void* workspace, size_t workspace_bytes, void* stream) {
+  VFX_ENTER(e);
+  VFX_REQUIRE(mel && wav_out && B > 0 && T > 0 && workspace, "vocoder: bad arguments");
+  Bump ws(workspace, workspace_bytes);
+  Ctx c{e, (cudaStream_t)stream, &ws, false, VFX_MODE_EVAL};
+  int r = vocoder_forward(c, mel, B, T, input_is_log, wav_out, trim_len, scale);
+  if (r != VFX_OK) return r;
+  VFX_FINISH(c, ws);
+}
+
+int vfx_vocoder_cond(vfx_engine* e, const float* cond, int B, int Tc, float* wav_out, int trim_len, float scale,
+                     void* workspace, size_t workspace_bytes, void* stream) {
+  VFX_ENTER(e);
+  VFX_REQUIRE(cond && wav_out && B > 0 && Tc >= 4 && workspace, "vocoder_cond: bad arguments");
+  Bump ws(workspace, workspace_bytes);
+  Ctx c{e, (cudaStream_t)stream, &ws, false, VFX_MODE_EVAL};
+  void* op = ws.raw((size_t)B * Tc * 128 * e->esz());
+  if (ws.overflow) { set_error("workspace too small"); return VFX_ERR_WORKSPACE; }
+  int r = cast_rows(cond, (long long)B * Tc * 128, op, e->precision, c.st);
+  if (r != VFX_OK) return r;
+  r = vocoder_generator(c, op, B, Tc, wav_out, trim_len, scale);
+  if (r != VFX_OK) return r;
+  VFX_FINISH(c, ws);
+}
+
+int vfx_restore(vfx_engine* e, const float* wav, int B, int L, int mode, const uint8_t* drop_masks,
+                float* wav_out, void* workspace, size_t workspace_bytes, void* stream) {
+  VFX_ENTER(e);
+  VFX_REQUIRE(wav && wav_out && B > 0 && workspace, "restore: bad arguments");
+  VFX_REQUIRE(mode == VFX_MODE_EVAL || mode == VFX_MODE_TRAIN_BN, "restore: bad mode %d", mode);
+  VFX_REQUIRE(L > 1024, "restore: L=%d must exceed 1024 samples", L);
+  Bump ws(workspace, workspace_bytes);
+  Ctx c{e, (cudaStream_t)stream, &ws, false, mode};
+  int r = restore_forward(c, wav, B, L, drop_masks, wav_out);
+  if (r != VFX_OK) return r;
+  VFX_FINISH(c, ws);
+}
+
+int vfx_hf_cut(vfx_engine* e, const float* wav, int B, int L, float ratio, float* wav_out, int* cut_bins,
+               void* workspace, size_t workspace_bytes, void* stream) {
+  VFX_ENTER(e);
+  return hf_cut(wav, B, L, ratio, e->d_window, e->d_tw, wav_out, cut_bins, workspace, workspace_bytes,
+                (cudaStream_t)stream);
+}
+
+int vfx_conv_gemm(int precision, int impl, const vfx_conv_desc* d, void* stream) {
+  VFX_REQUIRE(d, "conv_gemm: null descriptor");
+  if (impl == 1) {
+    VFX_REQUIRE(precision == VFX_PREC_BF16, "conv_gemm: tcgen05 implementation is bf16 only");
+    return conv_gemm_tc(*d, (cudaStream_t)stream);
+  }
+  return conv_gemm_simt(precision, *d, (cudaStream_t)stream);
+}
+
+int vfx_gru_layer(const float* gi, const float* whh_t, const float* bhh, int B, int T, float* out, void* stream) {
+  return gru_layer(gi, whh_t, bhh, B, T, out, (cudaStream_t)stream);
+}
+
+}  // extern "C"

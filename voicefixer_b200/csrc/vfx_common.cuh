@@ -1,0 +1,100 @@
+// Shared declarations of the vfx_b200 CUDA library (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+#include "../../include/vfx_b200.h"
+
+namespace vfx {
+
+void set_error(const char* fmt, ...);
+
+#define VFX_CUDA_CHECK(expr)                                                          \
+  do {                                                                                \
+    cudaError_t _e = (expr);                                                          \
+    if (_e != cudaSuccess) {                                                          \
+      vfx::set_error("%s:%d CUDA error %s: %s", __FILE__, __LINE__, #expr,           \
+                     cudaGetErrorString(_e));                                         \
+      return VFX_ERR_CUDA;                                                            \
+    }                                                                                 \
+  } while (0)
+
+#define VFX_LAUNCH_CHECK() VFX_CUDA_CHECK(cudaGetLastError())
+
+#define VFX_REQUIRE(cond, ...)                                                        \
+  do {                                                                                \
+    if (!(cond)) {                                                                    \
+      vfx::set_error(__VA_ARGS__);                                                    \
+      return VFX_ERR_INVALID;                                                         \
+    }                                                                                 \
+  } while (0)
+
+static inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+// ------------------------------------------------------------------ device helpers
+__device__ __forceinline__ float to_f(float v) { return v; }
+__device__ __forceinline__ float to_f(__nv_bfloat16 v) { return __bfloat162float(v); }
+template <typename T> __device__ __forceinline__ T from_f(float v);
+template <> __device__ __forceinline__ float from_f<float>(float v) { return v; }
+template <> __device__ __forceinline__ __nv_bfloat16 from_f<__nv_bfloat16>(float v) {
+  return __float2bfloat16_rn(v);
+}
+
+__device__ __forceinline__ float apply_act(float v, int act, float p) {
+  switch (act) {
+    case VFX_ACT_LRELU: return v > 0.f ? v : v * p;
+    case VFX_ACT_ELU: return v > 0.f ? v : expm1f(v);
+    case VFX_ACT_LRELU_XSINX: {
+      float u = v > 0.f ? v : v * p;
+      return u + sinf(u);
+    }
+    case VFX_ACT_SIGMOID: return 1.f / (1.f + expf(-v));
+    default: return v;
+  }
+}
+
+// ------------------------------------------------------------------ kernels (host launchers)
+int conv_gemm_simt(int precision, const vfx_conv_desc& d, cudaStream_t st);
+int conv_gemm_tc(const vfx_conv_desc& d, cudaStream_t st);   // tcgen05, bf16
+
+// y = act(scale[b][c]*x + shift[b][c]); x fp32 [B][P][C] (row pitch ldx), y operand type.
+// bn_C == 1: single-channel BN (scale[b][0]).  stat_sB: element stride between items (0 = shared).
+int bn_act(int precision, const float* x, long long x_sB, long long ldx, int B, long long P, int C,
+           const float* scale, const float* shift, int bn_C, int stat_sB, int act, float act_param,
+           void* y, long long y_sB, long long ldy, cudaStream_t st);
+// per-item biased batch statistics -> scale/shift [B][C] (train-mode BN, eps 1e-5)
+// acc: scratch of 2*B*bn_C doubles.
+int bn_stats(const float* x, long long x_sB, long long ldx, int B, long long P, int C, int bn_C,
+             const float* gamma, const float* beta, float* scale, float* shift, double* acc,
+             cudaStream_t st);
+int dropout_apply(float* x, const uint8_t* keep, long long n, cudaStream_t st);
+int avgpool2x2(const float* x, long long x_sB, long long x_sH, long long x_sW, int B, int H, int W,
+               int C, float* y, cudaStream_t st);
+int stft_mel(const float* wav, int B, int L, int T, const float* window, const float2* tw,
+             const float* fbT, const int* fb_start, const int* fb_len, float* mel, float* sp,
+             cudaStream_t st);
+int gru_layer(const float* gi, const float* whh_t, const float* bhh, int B, int T, float* out,
+              cudaStream_t st);
+// denoiser tail: clean = sigmoid(lin)*mel ; x = log10(clip(clean)); unet_in[b][t][f<127][2]
+int mask_log_pack(const float* lin_sig, const float* mel, int B, int T, int Tp, float* xlog,
+                  float* unet_in, cudaStream_t st);
+// unet head: out[b][t][f] = (f<127 ? bias + sum_c w[c]*x[b][t][f][c] : 0) + xlog[b][t][f]
+int unet_head(const float* x, int B, int T, int Tp, const float* w, const float* bias,
+              const float* xlog, float* out, cudaStream_t st);
+// vocoder conditions: (from_log) / weight, dB, normalise, tail pad of -4 -> cond [B][Tc][128]
+// tab = mel_weight[128] ++ [min_level] (fp32, computed by the host exactly as the reference does)
+int voc_normalize(const float* mel, int B, int T, int Tc, int input_is_log, const float* tab,
+                  void* cond, int precision, cudaStream_t st);
+int cast_rows(const float* x, long long n, void* y, int precision, cudaStream_t st);
+// rows [0,3) and [3+L, L+6) of a [B][L+6][C] operand buffer <- reflection of the interior
+int reflect_pad3(void* buf, int B, int L, int C, int precision, cudaStream_t st);
+// final conv: lrelu0.2 -> reflect pad 3 -> conv k7 (64->1) -> tanh -> trim -> *scale
+int voc_post(const float* x, int B, int L, const float* w, const float* bias, int lo, int out_len,
+             float scale, float* out, cudaStream_t st);
+int hf_cut(const float* wav, int B, int L, float ratio, const float* window, const float2* tw,
+           float* out, int* cut_bins, void* ws, size_t ws_bytes, cudaStream_t st);
+size_t hf_cut_workspace(int B, int L);
+
+}  // namespace vfx

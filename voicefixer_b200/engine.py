@@ -1,0 +1,184 @@
+"""Python wrapper of the C-ABI engine: device memory, streams and weight upload (plumbing only).
+
+All compute goes through libvfx_b200.so; torch is used for device buffers, the current CUDA
+stream and (in parallel.py) torch.distributed."""
+import ctypes
+import os
+import numpy as np
+import torch
+
+from . import _lib
+from .weights import pack_analysis, pack_vocoder
+
+ALIGN = 256
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def default_precision():
+    return os.environ.get("VFX_PRECISION", "fp32")
+
+
+class Engine:
+    """One engine per process / GPU.  `ana`, `voc`: reference-layout state dicts (CPU tensors)."""
+
+    def __init__(self, ana=None, voc=None, device=None, precision=None, packed=None):
+        if not torch.cuda.is_available():
+            raise RuntimeError("voicefixer_b200 needs a CUDA device (B200, sm_100a); there is no CPU path")
+        self.lib = _lib.load()
+        self.device = torch.cuda.current_device() if device is None else int(device)
+        self.precision = precision or default_precision()
+        if self.precision not in _lib.PREC:
+            raise ValueError(f"precision must be one of {list(_lib.PREC)}")
+        h = ctypes.c_void_p()
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.vfx_engine_create(ctypes.byref(h), self.device, _lib.PREC[self.precision]),
+                       "vfx_engine_create")
+        self.h = h
+        self._ws = None
+        self.arena = None
+        self.table = None
+        if packed is None and ana is not None:
+            packed = {}
+            packed.update(pack_analysis(ana, self.precision))
+            packed.update(pack_vocoder(voc, self.precision))
+        if packed is not None:
+            self.upload(packed)
+
+    # ------------------------------------------------------------------ weights
+    @staticmethod
+    def layout(packed):
+        """[(name, offset, nbytes)] and total bytes of the single weight arena."""
+        table, off = [], 0
+        for name in sorted(packed):
+            t = packed[name]
+            nbytes = t.numel() * t.element_size()
+            table.append((name, off, nbytes))
+            off += (nbytes + ALIGN - 1) // ALIGN * ALIGN
+        return table, off
+
+    def upload(self, packed):
+        table, total = self.layout(packed)
+        host = torch.empty(total, dtype=torch.uint8).pin_memory()
+        for name, off, nbytes in table:
+            host[off:off + nbytes] = packed[name].contiguous().view(torch.uint8).reshape(-1)
+        arena = torch.empty(total, dtype=torch.uint8, device=f"cuda:{self.device}")
+        arena.copy_(host, non_blocking=False)
+        self.attach(arena, table)
+
+    def attach(self, arena, table):
+        """Registers views of an arena that is already on this device (e.g. after an NCCL broadcast)."""
+        self.arena, self.table = arena, table
+        base = arena.data_ptr()
+        for name, off, nbytes in table:
+            _lib.check(self.lib.vfx_engine_set_tensor(self.h, name.encode(), ctypes.c_void_p(base + off), nbytes),
+                       f"set_tensor({name})")
+        _lib.check(self.lib.vfx_engine_finalize(self.h), "vfx_engine_finalize")
+
+    def set_option(self, key, value):
+        _lib.check(self.lib.vfx_engine_set_option(self.h, key.encode(), int(value)), "set_option")
+
+    def __del__(self):
+        try:
+            if getattr(self, "h", None):
+                self.lib.vfx_engine_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------ workspace
+    def _workspace(self, nbytes):
+        if nbytes == 0:
+            raise _lib.VfxError("workspace query failed: " + self.lib.vfx_last_error().decode())
+        if self._ws is None or self._ws.numel() < nbytes:
+            self._ws = None
+            self._ws = torch.empty(nbytes, dtype=torch.uint8, device=f"cuda:{self.device}")
+        return self._ws
+
+    def workspace_bytes(self, B, L):
+        return int(self.lib.vfx_workspace_bytes(self.h, B, L))
+
+    def _dev(self, x):
+        if isinstance(x, np.ndarray):
+            x = torch.from_numpy(np.ascontiguousarray(x))
+        return x.to(device=f"cuda:{self.device}", dtype=torch.float32).contiguous()
+
+    # ------------------------------------------------------------------ the five seams
+    def frontend(self, wav, return_sp=False):
+        """wav (B, L) -> mel (B, T, 128) [, sp (B, T, 1025)]."""
+        wav = self._dev(wav)
+        B, L = wav.shape
+        T = 1 + L // 441
+        mel = torch.empty(B, T, 128, device=wav.device)
+        sp = torch.empty(B, T, 1025, device=wav.device) if return_sp else None
+        _lib.check(self.lib.vfx_frontend_mel(self.h, _ptr(wav), B, L, _ptr(mel), _ptr(sp), _stream()), "vfx_frontend_mel")
+        return (mel, sp) if return_sp else mel
+
+    def analysis(self, mel, mode=0, drop_masks=None):
+        """mel (B, T, 128) linear -> log10 mel (B, T, 128)."""
+        mel = self._dev(mel)
+        B, T, F = mel.shape
+        if F != 128:
+            raise AssertionError("mel must have 128 bins")
+        out = torch.empty_like(mel)
+        ws = self._workspace(int(self.lib.vfx_workspace_bytes_frames(self.h, B, T)))
+        dm = None
+        if drop_masks is not None:
+            dm = drop_masks.to(device=mel.device, dtype=torch.uint8).contiguous()
+            assert tuple(dm.shape) == (2, B, T, 512)
+        _lib.check(self.lib.vfx_analysis(self.h, _ptr(mel), B, T, int(mode), _ptr(dm), _ptr(out), _ptr(ws), ws.numel(),
+                                         _stream()), "vfx_analysis")
+        return out
+
+    def vocoder(self, mel, input_is_log=False, trim_len=-1, scale=1.0):
+        """mel (B, T, 128) -> wav (B, out_len)."""
+        mel = self._dev(mel)
+        B, T, F = mel.shape
+        if F != 128:
+            raise AssertionError("mel must have 128 bins")
+        S = (T + T % 2 + 4) * 441
+        out = torch.empty(B, S if trim_len < 0 else trim_len, device=mel.device)
+        ws = self._workspace(int(self.lib.vfx_workspace_bytes_frames(self.h, B, T)))
+        _lib.check(self.lib.vfx_vocoder(self.h, _ptr(mel), B, T, int(bool(input_is_log)), _ptr(out), int(trim_len),
+                                        float(scale), _ptr(ws), ws.numel(), _stream()), "vfx_vocoder")
+        return out
+
+    def vocoder_cond(self, cond, trim_len=-1, scale=1.0):
+        """normalised conditions (B, Tc, 128) [channels-last] -> wav (B, Tc*441)."""
+        cond = self._dev(cond)
+        B, Tc, F = cond.shape
+        out = torch.empty(B, Tc * 441 if trim_len < 0 else trim_len, device=cond.device)
+        ws = self._workspace(int(self.lib.vfx_workspace_bytes_frames(self.h, B, Tc)))
+        _lib.check(self.lib.vfx_vocoder_cond(self.h, _ptr(cond), B, Tc, _ptr(out), int(trim_len), float(scale), _ptr(ws),
+                                             ws.numel(), _stream()), "vfx_vocoder_cond")
+        return out
+
+    def restore(self, wav, mode=0, drop_masks=None, out=None):
+        """wav (B, L) on device -> restored wav (B, L) on device (one launch sequence)."""
+        wav = self._dev(wav)
+        B, L = wav.shape
+        if out is None:
+            out = torch.empty_like(wav)
+        ws = self._workspace(self.workspace_bytes(B, L))
+        dm = None
+        if drop_masks is not None:
+            dm = drop_masks.to(device=wav.device, dtype=torch.uint8).contiguous()
+        _lib.check(self.lib.vfx_restore(self.h, _ptr(wav), B, L, int(mode), _ptr(dm), _ptr(out), _ptr(ws), ws.numel(),
+                                        _stream()), "vfx_restore")
+        return out
+
+    def hf_cut(self, wav, ratio=0.95):
+        wav = self._dev(wav)
+        B, L = wav.shape
+        out = torch.empty(B, 512 * (L // 512), device=wav.device)
+        cut = torch.empty(B, dtype=torch.int32, device=wav.device)
+        ws = self._workspace(max(1 << 20, 64 * B * (L + 4096)))
+        _lib.check(self.lib.vfx_hf_cut(self.h, _ptr(wav), B, L, float(ratio), _ptr(out), _ptr(cut), _ptr(ws), ws.numel(),
+                                       _stream()), "vfx_hf_cut")
+        return out, cut
