@@ -48,8 +48,14 @@ int vfx_engine_destroy(vfx_engine* e);
  * against what the engine expects when it is first used).  Names and layouts: DESIGN.md §3.
  * Replaces torch.load + load_state_dict: voicefixer/base.py:15-30, voicefixer/vocoder/base.py:24-32. */
 int vfx_engine_set_tensor(vfx_engine* e, const char* name, const void* dev_ptr, size_t bytes);
-/* Engine options: "use_tc" (BF16 only; 1 = tcgen05 kernel [default], 0 = SIMT cross-check). */
+/* Engine options: "use_tc" (BF16 only; 1 = tcgen05 kernel [default], 0 = SIMT cross-check),
+ * "profile" (0/1, see vfx_profile_report). */
 int vfx_engine_set_option(vfx_engine* e, const char* key, int value);
+/* Number of CUDA kernels this library has launched in this process (bench.py's gpu_launches). */
+unsigned long long vfx_launch_count(void);
+/* With option "profile" = 1 every launch group is bracketed by CUDA events on the call's stream;
+ * this synchronises, writes one line per tag "tag count total_ms flops bytes" and clears the log. */
+int vfx_profile_report(vfx_engine* e, char* buf, size_t cap);
 /* Resolve every name the engine needs; returns VFX_ERR_MISSING_WEIGHT and lists them otherwise. */
 int vfx_engine_finalize(vfx_engine* e);
 

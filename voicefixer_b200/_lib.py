@@ -41,6 +41,8 @@ SIGNATURES = {
     "vfx_engine_set_tensor": (_i, [_vp, _c.c_char_p, _vp, _sz]),
     "vfx_engine_set_option": (_i, [_vp, _c.c_char_p, _i]),
     "vfx_engine_finalize": (_i, [_vp]),
+    "vfx_launch_count": (_c.c_ulonglong, []),
+    "vfx_profile_report": (_i, [_vp, _c.c_char_p, _sz]),
     "vfx_workspace_bytes": (_sz, [_vp, _i, _i]),
     "vfx_workspace_bytes_frames": (_sz, [_vp, _i, _i]),
     "vfx_frontend_mel": (_i, [_vp, _vp, _i, _i, _vp, _vp, _vp]),

@@ -20,7 +20,12 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
+unsigned long long g_launches = 0;
+
 struct Tensor { const void* p; size_t bytes; };
+
+// per-tag CUDA-event timing of the launch sequence (option "profile")
+struct ProfRec { std::string tag; cudaEvent_t a, b; double flops, bytes; };
 
 }  // namespace vfx
 
@@ -33,6 +38,9 @@ struct vfx_engine {
   float* d_window = nullptr;    // periodic Hann, 2048
   float2* d_tw = nullptr;       // exp(-2 pi i k / 2048), k < 1024
   std::vector<std::string> missing;
+  int profile = 0;
+  std::vector<vfx::ProfRec> prof;
+  std::string prof_report;
   size_t esz() const { return precision == VFX_PREC_BF16 ? 2 : 4; }
 };
 
@@ -69,6 +77,23 @@ struct Ctx {
   int prec() const { return e->precision; }
 };
 
+struct ProfScope {
+  Ctx& c; bool on;
+  ProfScope(Ctx& c_, const char* tag, double flops, double bytes) : c(c_), on(false) {
+    if (c.dry || !c.e->profile) return;
+    ProfRec r; r.tag = tag; r.flops = flops; r.bytes = bytes;
+    if (cudaEventCreate(&r.a) != cudaSuccess || cudaEventCreate(&r.b) != cudaSuccess) return;
+    cudaEventRecord(r.a, c.st);
+    c.e->prof.push_back(r);
+    on = true;
+  }
+  ~ProfScope() { if (on) cudaEventRecord(c.e->prof.back().b, c.st); }
+};
+
+double conv_flops(const vfx_conv_desc& d) {
+  return 2.0 * d.B * d.Hq * d.Wq * (double)d.N * d.Cin * d.ntaps;
+}
+
 #define VFX_TRY(expr) do { int _r = (expr); if (_r != VFX_OK) return _r; } while (0)
 
 const void* get(Ctx& c, const std::string& name, size_t bytes) {
@@ -91,9 +116,10 @@ const void* getw(Ctx& c, const std::string& name, size_t n, int prec) {
   return get(c, name, n * (prec == VFX_PREC_BF16 ? 2 : 4));
 }
 
-int run_conv(Ctx& c, int prec, const vfx_conv_desc& d) {
+int run_conv(Ctx& c, int prec, const vfx_conv_desc& d, const char* tag = "conv") {
   if (c.dry) return VFX_OK;
   if (c.rc != VFX_OK) return c.rc;
+  ProfScope ps(c, tag, conv_flops(d), 0.0);
   if (prec == VFX_PREC_BF16 && c.e->use_tc) {
     int r = conv_gemm_tc(d, c.st);
     if (r != VFX_ERR_UNSUPPORTED) return r;
@@ -158,6 +184,7 @@ int bn_act_op(Ctx& c, int prec, const std::string& bn, int bn_C, const float* x,
   BnRef r;
   VFX_TRY(bn_resolve(c, bn, bn_C, x, x_sB, ldx, B, P, C, &r));
   if (c.dry) return VFX_OK;
+  ProfScope ps(c, "bn_act", 0.0, (double)B * P * C * (4 + (prec == VFX_PREC_BF16 ? 2 : 4)));
   return bn_act(prec, x, x_sB, ldx, B, P, C, r.scale, r.shift, bn_C, r.stat_sB, act, slope, y,
                 (long long)P * C, C, c.st);
 }
@@ -176,7 +203,7 @@ int conv_block(Ctx& c, const std::string& p, const float* in, long long ld_in, i
     vfx_conv_desc d = conv_base(s.opA, B, H, W, Cin, getw(c, p + ".conv1.w", (size_t)9 * Cout * Cin, prec), Cout);
     taps3x3(d, (long long)Cout * Cin);
     set_raw(d, s.rawH, Cout, 0);
-    VFX_TRY(run_conv(c, prec, d));
+    VFX_TRY(run_conv(c, prec, d, "unet.conv3x3"));
   }
   VFX_TRY(bn_act_op(c, prec, p + ".bn2", Cout, s.rawH, P * Cout, Cout, B, P, Cout, VFX_ACT_LRELU, 0.01f, s.opH));
   const float* res = in; long long ld_res = ld_in;
@@ -191,7 +218,7 @@ int conv_block(Ctx& c, const std::string& p, const float* in, long long ld_in, i
     d.ntaps = 1;
     d.bias = getf(c, p + ".sc.b", Cout);
     set_raw(d, s.rawS, Cout, 0);
-    VFX_TRY(run_conv(c, prec, d));
+    VFX_TRY(run_conv(c, prec, d, "unet.shortcut"));
     res = s.rawS; ld_res = Cout;
   }
   {
@@ -199,7 +226,7 @@ int conv_block(Ctx& c, const std::string& p, const float* in, long long ld_in, i
     taps3x3(d, (long long)Cout * Cout);
     set_res(d, res, ld_res, 0);
     set_raw(d, out, ld_out, 0);
-    VFX_TRY(run_conv(c, prec, d));
+    VFX_TRY(run_conv(c, prec, d, "unet.conv3x3"));
   }
   return c.rc;
 }
@@ -236,6 +263,7 @@ int unet_forward(Ctx& c, const float* unet_in, int B, int Tp, float** feat_out) 
       if (j == 1) VFX_TRY(conv_block(c, name, x, Cx, B, H, W, Cx, C, skip, 2 * C, s));
       else VFX_TRY(conv_block(c, name, skip, 2 * C, B, H, W, C, C, skip, 2 * C, s));
     }
+    ProfScope ps(c, "unet.pool", 0.0, (double)B * H * W * C * 5.0);
     if (!c.dry) VFX_TRY(avgpool2x2(skip, (long long)H * W * 2 * C, (long long)W * 2 * C, 2 * C, B, H, W, C, pool[l], c.st));
     x = pool[l]; Cx = C;
   }
@@ -267,7 +295,7 @@ int unet_forward(Ctx& c, const float* unet_in, int B, int Tp, float** feat_out) 
           }
         d.ntaps = n;
         set_raw(d, cat[l], 2 * Cout, 0);
-        VFX_TRY(run_conv(c, prec, d));
+        VFX_TRY(run_conv(c, prec, d, "unet.convT"));
       }
     // conv_block2..5: first consumes the concat tensor (2C -> C, with shortcut)
     float* dl = pool[l];                          // dense [B][OH][OW][Cout]: reuse? sizes differ -> own buffer
@@ -296,6 +324,7 @@ int linear(Ctx& c, const void* a, long long M, int K, const std::string& p, int 
   if (out_act) set_act(d, out_act, N, 0, act, 0.f);
   if (c.dry) return c.rc;
   if (c.rc != VFX_OK) return c.rc;
+  ProfScope ps(c, "dn.linear", conv_flops(d), 0.0);
   return conv_gemm_simt(VFX_PREC_FP32, d, c.st);
 }
 
@@ -317,8 +346,8 @@ int bn_gru(Ctx& c, const std::string& p, const float* x, int B, int T, float* op
     const float* whh = getf(c, q + ".whh_t", (size_t)2 * 256 * 768);
     const float* bhh = getf(c, q + ".bhh", 2 * 768);
     if (!c.dry && c.rc == VFX_OK) {
-      VFX_TRY(conv_gemm_simt(VFX_PREC_FP32, d, c.st));
-      VFX_TRY(gru_layer(gi, whh, bhh, B, T, outs[layer], c.st));
+      { ProfScope ps(c, "dn.gru_in", conv_flops(d), 0.0); VFX_TRY(conv_gemm_simt(VFX_PREC_FP32, d, c.st)); }
+      { ProfScope ps(c, "dn.gru", 2.0 * M * 2 * 768 * 256, 0.0); VFX_TRY(gru_layer(gi, whh, bhh, B, T, outs[layer], c.st)); }
     }
     in = outs[layer];
   }
@@ -405,7 +434,7 @@ int vocoder_generator(Ctx& c, const void* cond, int B, int Tc, float* wav_out, i
     } else {
       set_act(d, out, 512, 0, VFX_ACT_ELU, 0.f);
     }
-    VFX_TRY(run_conv(c, prec, d));
+    VFX_TRY(run_conv(c, prec, d, "voc.condnet"));
     in = out; Cin = 512;
   }
   if (!c.dry) VFX_TRY(reflect_pad3((void*)in, B, Tc, 512, prec, c.st));
@@ -417,12 +446,16 @@ int vocoder_generator(Ctx& c, const void* cond, int B, int Tc, float* wav_out, i
     for (int k = 0; k < 7; ++k) { d.dw[k] = k; d.w_off[k] = (long long)k * 1024 * 512; }
     d.bias = getf(c, "voc.pre.b", 1024);
     set_act(d, U, 1024, 0, VFX_ACT_LRELU_XSINX, 0.2f);
-    VFX_TRY(run_conv(c, prec, d));
+    VFX_TRY(run_conv(c, prec, d, "voc.pre"));
   }
   long long Lin = Tc;
   for (int j = 0; j < 4; ++j) {
     const int Ci = VOC_CIN[j], Co = VOC_COUT[j], u = VOC_U[j];
     const long long Lout = Lin * u;
+    char up_tag[32], c1_tag[32], c2_tag[32];
+    snprintf(up_tag, sizeof(up_tag), "voc.up%d", j);
+    snprintf(c1_tag, sizeof(c1_tag), "voc.rs%d.c1", j);
+    snprintf(c2_tag, sizeof(c2_tag), "voc.rs%d.c2", j);
     // ---- UpsampleNet: ConvTranspose1d(k=2u, s=u, p, op) as two phase-group GEMMs (modules.py:451-459)
     snprintf(name, sizeof(name), "voc.up%d", j);
     {
@@ -441,7 +474,7 @@ int vocoder_generator(Ctx& c, const void* cond, int B, int Tc, float* wav_out, i
         d.bias = bias; d.bias_mod = Co;
         set_raw(d, X, Co, 0);
         set_act(d, A0, Co, 0, VFX_ACT_LRELU, 0.01f);
-        VFX_TRY(run_conv(c, prec, d));
+        VFX_TRY(run_conv(c, prec, d, up_tag));
       }
     }
     // ---- ResStack: 8 x (x + conv_k3_d1(lrelu(conv_k3_d3^i(lrelu(x))))), modules.py:550-576,592-595
@@ -455,7 +488,7 @@ int vocoder_generator(Ctx& c, const void* cond, int B, int Tc, float* wav_out, i
         for (int k = 0; k < 3; ++k) { d.dw[k] = (k - 1) * dil; d.w_off[k] = (long long)k * Co * Co; }
         d.bias = getf(c, p + ".c1.b", Co);
         set_act(d, Hh, Co, 0, VFX_ACT_LRELU, 0.01f);
-        VFX_TRY(run_conv(c, prec, d));
+        VFX_TRY(run_conv(c, prec, d, c1_tag));
       }
       {
         vfx_conv_desc d = conv_base(Hh, B, 1, (int)Lout, Co, getw(c, p + ".c2.w", (size_t)3 * Co * Co, prec), Co);
@@ -466,7 +499,7 @@ int vocoder_generator(Ctx& c, const void* cond, int B, int Tc, float* wav_out, i
         set_raw(d, X, Co, 0);
         if (i < 7) set_act(d, A0, Co, 0, VFX_ACT_LRELU, 0.01f);
         else if (j < 3) set_act(d, U, Co, 0, VFX_ACT_LRELU_XSINX, 0.2f);   // act + next UpsampleNet's x+sin x
-        VFX_TRY(run_conv(c, prec, d));
+        VFX_TRY(run_conv(c, prec, d, c2_tag));
       }
     }
     Lin = Lout;
@@ -481,6 +514,7 @@ int vocoder_generator(Ctx& c, const void* cond, int B, int Tc, float* wav_out, i
   }
   const float* pw = getf(c, "voc.post.w", 7 * 64);
   const float* pb = getf(c, "voc.post.b", 1);
+  ProfScope ps(c, "voc.post", 2.0 * B * out_len * 7 * 64, (double)B * S * 64 * 4);
   if (!c.dry && c.rc == VFX_OK) VFX_TRY(voc_post(X, B, (int)S, pw, pb, lo, (int)out_len, scale, wav_out, c.st));
   c.ws->reset(m0);
   return c.rc;
@@ -504,6 +538,7 @@ int frontend_forward(Ctx& c, const float* wav, int B, int L, float* mel, float* 
   const int* fs = (const int*)get(c, "fe.fb_start", 128 * 4);
   const int* fl = (const int*)get(c, "fe.fb_len", 128 * 4);
   if (c.dry || c.rc != VFX_OK) return c.rc;
+  ProfScope ps(c, "fe.stft_mel", (double)B * T * (5.0 * 1024 * 10 + 2.0 * 2050), (double)B * L * 4);
   return stft_mel(wav, B, L, T, c.e->d_window, c.e->d_tw, fbT, fs, fl, mel, sp, c.st);
 }
 
@@ -566,9 +601,39 @@ int vfx_engine_destroy(vfx_engine* e) {
   return VFX_OK;
 }
 
+unsigned long long vfx_launch_count(void) { return vfx::g_launches; }
+
+int vfx_profile_report(vfx_engine* e, char* buf, size_t cap) {
+  VFX_REQUIRE(e && buf && cap > 0, "profile_report: bad arguments");
+  VFX_CUDA_CHECK(cudaSetDevice(e->device));
+  VFX_CUDA_CHECK(cudaDeviceSynchronize());
+  struct Agg { double ms = 0, flops = 0, bytes = 0; long n = 0; };
+  std::vector<std::pair<std::string, Agg>> agg;
+  for (auto& r : e->prof) {
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, r.a, r.b);
+    cudaEventDestroy(r.a); cudaEventDestroy(r.b);
+    size_t i = 0;
+    for (; i < agg.size(); ++i) if (agg[i].first == r.tag) break;
+    if (i == agg.size()) agg.push_back({r.tag, Agg()});
+    agg[i].second.ms += ms; agg[i].second.flops += r.flops; agg[i].second.bytes += r.bytes; agg[i].second.n++;
+  }
+  e->prof.clear();
+  std::string out;
+  char line[256];
+  for (auto& a : agg) {
+    snprintf(line, sizeof(line), "%s %ld %.6f %.6e %.6e\n", a.first.c_str(), a.second.n, a.second.ms, a.second.flops,
+             a.second.bytes);
+    out += line;
+  }
+  snprintf(buf, cap, "%s", out.c_str());
+  return VFX_OK;
+}
+
 int vfx_engine_set_option(vfx_engine* e, const char* key, int value) {
   VFX_REQUIRE(e && key, "set_option: null argument");
   if (!strcmp(key, "use_tc")) { e->use_tc = value; return VFX_OK; }
+  if (!strcmp(key, "profile")) { e->profile = value; return VFX_OK; }
   set_error("set_option: unknown key '%s'", key);
   return VFX_ERR_INVALID;
 }

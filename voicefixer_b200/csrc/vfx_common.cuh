@@ -21,7 +21,9 @@ void set_error(const char* fmt, ...);
     }                                                                                 \
   } while (0)
 
-#define VFX_LAUNCH_CHECK() VFX_CUDA_CHECK(cudaGetLastError())
+extern unsigned long long g_launches;   // kernels launched by this library (bench.py's gpu_launches)
+#define VFX_LAUNCH_CHECK()                                                            \
+  do { ++vfx::g_launches; VFX_CUDA_CHECK(cudaGetLastError()); } while (0)
 
 #define VFX_REQUIRE(cond, ...)                                                        \
   do {                                                                                \

@@ -84,6 +84,22 @@ class Engine:
     def set_option(self, key, value):
         _lib.check(self.lib.vfx_engine_set_option(self.h, key.encode(), int(value)), "set_option")
 
+    def profile(self, on=True):
+        self.set_option("profile", 1 if on else 0)
+
+    def profile_report(self):
+        """{tag: dict(count, ms, flops, bytes)} of everything launched since the last report."""
+        buf = ctypes.create_string_buffer(1 << 16)
+        _lib.check(self.lib.vfx_profile_report(self.h, buf, len(buf)), "vfx_profile_report")
+        rep = {}
+        for line in buf.value.decode().splitlines():
+            tag, n, ms, fl, by = line.split()
+            rep[tag] = dict(count=int(n), ms=float(ms), flops=float(fl), bytes=float(by))
+        return rep
+
+    def launch_count(self):
+        return int(self.lib.vfx_launch_count())
+
     def __del__(self):
         try:
             if getattr(self, "h", None):
