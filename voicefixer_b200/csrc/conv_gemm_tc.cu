@@ -1,5 +1,402 @@
-// tcgen05 implementation of the conv GEMM (placeholder until the TMA/TMEM kernel lands).
+// Channels-last shifted-window convolution GEMM on the 5th-gen tensor cores (sm_100a):
+// TMA-staged bf16 tiles -> tcgen05.mma (fp32 accumulators in TMEM) -> fused epilogue.
+//
+// Same contract as conv_gemm_simt (vfx_conv_desc); this is the production path behind the
+// reference's Conv1d/Conv2d/ConvTranspose layers (see conv_gemm_simt.cu for the file:line list).
+//
+//   D[128 positions][Ntile channels] += A_tap[128][KC] * W_tap[Ntile][KC]^T     (K-major, SW128/SW64)
+//
+// * One M-tile = a (th x tw) patch of the output grid of one item, th*tw = 128.  Every tap is a
+//   TMA box load of the same patch shifted by (dh, dw); rows/columns outside the tensor are
+//   zero-filled by TMA, which IS the convolution's zero padding (no im2col, no halo logic).
+// * Persistent CTAs (one per SM), static round-robin tile schedule, warp roles:
+//     warp 0   TMA producer (one elected lane)        warp 1   tcgen05.mma issuer (one lane)
+//     warp 2-5 epilogue: tcgen05.ld TMEM->registers, +bias, +residual(fp32), activation, stores
+//   smem ring of S stages (full/empty mbarriers) and 2 TMEM accumulator stages (tmem_full/empty)
+//   so the epilogue of tile i overlaps the MMAs of tile i+1.
+#include <cuda.h>
 #include "vfx_common.cuh"
+
 namespace vfx {
-int conv_gemm_tc(const vfx_conv_desc& d, cudaStream_t st) { (void)d; (void)st; return VFX_ERR_UNSUPPORTED; }
+
+namespace {
+
+constexpr int TILE_M = 128;
+constexpr int NUM_THREADS = 192;          // 6 warps
+constexpr int EPI_WARP0 = 2;
+
+struct TcParams {
+  // tile schedule
+  int B, Hq, Wq, tw_log2, th, n_tw, n_th, n_nt, Ntile, KC, n_kc, ntaps, stages;
+  long long total_tiles;
+  int dh[9], dw[9];
+  int w_row[9];             // first weight row of each tap (w_off / Cin)
+  // output mapping
+  int sh, rh, sw, rw, OH, OW, N;
+  float* out_raw; long long o_sB, o_sH, o_sW; int o_col;
+  __nv_bfloat16* out_act; long long oa_sB, oa_sH, oa_sW; int oa_col;
+  const float* bias; int bias_mod;
+  const float* residual; long long r_sB, r_sH, r_sW; int r_col;
+  int act; float act_param;
+  uint32_t idesc;           // tcgen05 instruction descriptor
+  uint32_t a_stage_bytes, b_stage_bytes;
+  uint32_t sbo16;           // stride-byte-offset >> 4 of the K-major swizzled layout (8 rows)
+  uint32_t layout_type;     // 2 = SWIZZLE_128B, 4 = SWIZZLE_64B
+  uint32_t tmem_cols;
+};
+
+// ------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
 }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra WAIT_DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "WAIT_DONE:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_mma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t* v) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+        "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+        "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// K-major swizzled shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout):
+// [0,14) start>>4, [16,30) LBO>>4 (unused for swizzled K-major: 1), [32,46) SBO>>4, [46,48) version=1,
+// [61,64) layout type.
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t sbo16, uint32_t layout_type) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(sbo16 & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)(layout_type & 7) << 61;
+  return d;
+}
+
+struct TileCoord { int b, h0, w0, n0; };
+__device__ __forceinline__ TileCoord decode_tile(const TcParams& p, long long tile) {
+  TileCoord t;
+  const int nt = (int)(tile % p.n_nt);
+  long long m = tile / p.n_nt;
+  const int iw = (int)(m % p.n_tw); m /= p.n_tw;
+  const int ih = (int)(m % p.n_th);
+  t.b = (int)(m / p.n_th);
+  t.h0 = ih * p.th; t.w0 = iw << p.tw_log2; t.n0 = nt * p.Ntile;
+  return t;
+}
+
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
+                    const __grid_constant__ TcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const uint32_t stage_bytes = p.a_stage_bytes + p.b_stage_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * stage_bytes);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + p.stages;
+  uint64_t* tmem_full = bars + 2 * p.stages;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmW)) : "memory");
+    for (int s = 0; s < p.stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], 128); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {   // TMEM allocation (whole warp), address published through smem
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(p.tmem_cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int k_steps = p.ntaps * p.n_kc;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      uint32_t s = 0, ph = 0;
+      for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        const TileCoord t = decode_tile(p, tile);
+        for (int tap = 0; tap < p.ntaps; ++tap) {
+          for (int kc = 0; kc < p.n_kc; ++kc) {
+            mbar_wait(&empty[s], ph ^ 1);
+            uint8_t* sa = smem + (size_t)s * stage_bytes;
+            mbar_expect_tx(&full[s], stage_bytes);
+            tma_load_4d(&tmA, &full[s], sa, kc * p.KC, t.w0 + p.dw[tap], t.h0 + p.dh[tap], t.b);
+            tma_load_2d(&tmW, &full[s], sa + p.a_stage_bytes, kc * p.KC, p.w_row[tap] + t.n0);
+            if (++s == (uint32_t)p.stages) { s = 0; ph ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      uint32_t s = 0, ph = 0, acc = 0, acc_ph = 0;
+      const int kk = p.KC / 16;                       // UMMA_K = 16 for bf16
+      for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        mbar_wait(&tmem_empty[acc], acc_ph ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * p.Ntile;
+        for (int ks = 0; ks < k_steps; ++ks) {
+          mbar_wait(&full[s], ph);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(smem + (size_t)s * stage_bytes);
+          const uint32_t b_addr = a_addr + p.a_stage_bytes;
+#pragma unroll 4
+          for (int k = 0; k < kk; ++k) {
+            const uint64_t ad = make_smem_desc(a_addr + k * 32, p.sbo16, p.layout_type);
+            const uint64_t bd = make_smem_desc(b_addr + k * 32, p.sbo16, p.layout_type);
+            tc_mma_bf16(d_tmem, ad, bd, p.idesc, (ks | k) ? 1u : 0u);
+          }
+          tc_commit(&empty[s]);                       // frees the smem stage when these MMAs retire
+          if (++s == (uint32_t)p.stages) { s = 0; ph ^= 1; }
+        }
+        tc_commit(&tmem_full[acc]);                   // accumulator ready for the epilogue
+        if (++acc == 2) { acc = 0; acc_ph ^= 1; }
+      }
+    }
+  } else {
+    // ===================== epilogue (4 warps = 128 TMEM lanes) =====================
+    const int sub = warp & 3;                         // TMEM sub-partition this warp may access
+    const int row = sub * 32 + lane;                  // accumulator row = position inside the patch
+    uint32_t acc = 0, acc_ph = 0;
+    for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      const TileCoord t = decode_tile(p, tile);
+      const int qh = t.h0 + (row >> p.tw_log2), qw = t.w0 + (row & ((1 << p.tw_log2) - 1));
+      const int oh = qh * p.sh + p.rh, ow = qw * p.sw + p.rw;
+      const bool valid = qh < p.Hq && qw < p.Wq && oh < p.OH && ow < p.OW;
+      mbar_wait(&tmem_full[acc], acc_ph);
+      tc_fence_after();
+      const uint32_t t_row = tmem_base + ((uint32_t)(sub * 32) << 16) + acc * p.Ntile;
+      for (int c0 = 0; c0 < p.Ntile; c0 += 32) {
+        uint32_t v[32];
+        tc_ld32(t_row + c0, v);
+        if (valid) {
+          const int n = t.n0 + c0;
+          float f[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+          if (p.bias) {
+            const float4* bp = reinterpret_cast<const float4*>(p.bias + (n % p.bias_mod));
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float4 b4 = __ldg(bp + j);
+              f[4 * j] += b4.x; f[4 * j + 1] += b4.y; f[4 * j + 2] += b4.z; f[4 * j + 3] += b4.w;
+            }
+          }
+          if (p.residual) {
+            const float4* rp = reinterpret_cast<const float4*>(
+                p.residual + (long long)t.b * p.r_sB + (long long)oh * p.r_sH + (long long)ow * p.r_sW + p.r_col + n);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float4 r4 = rp[j];
+              f[4 * j] += r4.x; f[4 * j + 1] += r4.y; f[4 * j + 2] += r4.z; f[4 * j + 3] += r4.w;
+            }
+          }
+          if (p.out_raw) {
+            float4* op = reinterpret_cast<float4*>(
+                p.out_raw + (long long)t.b * p.o_sB + (long long)oh * p.o_sH + (long long)ow * p.o_sW + p.o_col + n);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) op[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+          }
+          if (p.out_act) {
+            uint4* ap = reinterpret_cast<uint4*>(
+                p.out_act + (long long)t.b * p.oa_sB + (long long)oh * p.oa_sH + (long long)ow * p.oa_sW + p.oa_col + n);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              uint32_t w[4];
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                const float lo = apply_act(f[8 * j + 2 * q], p.act, p.act_param);
+                const float hi = apply_act(f[8 * j + 2 * q + 1], p.act, p.act_param);
+                __nv_bfloat162 h2 = __floats2bfloat162_rn(lo, hi);
+                w[q] = *reinterpret_cast<uint32_t*>(&h2);
+              }
+              ap[j] = make_uint4(w[0], w[1], w[2], w[3]);
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&tmem_empty[acc]);
+      if (++acc == 2) { acc = 0; acc_ph ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+int ilog2(int v) { int l = 0; while ((1 << l) < v) ++l; return l; }
+
+}  // namespace
+
+int conv_gemm_tc(const vfx_conv_desc& d, cudaStream_t st) {
+  // ---- shapes this kernel covers; everything else returns UNSUPPORTED (caller uses the SIMT kernel)
+  int KC = 0;
+  if (d.Cin % 64 == 0) KC = 64; else if (d.Cin == 32) KC = 32;
+  if (!KC) return VFX_ERR_UNSUPPORTED;
+  int Ntile = 0;
+  for (int c : {256, 128, 64, 32}) if (d.N % c == 0) { Ntile = c; break; }
+  if (!Ntile) return VFX_ERR_UNSUPPORTED;
+  if (d.ntaps < 1 || d.ntaps > 9) return VFX_ERR_UNSUPPORTED;
+  if (d.a_sW % 8 || d.a_sH % 8 || d.a_sB % 8 || ((uintptr_t)d.a & 15) || ((uintptr_t)d.w & 15)) return VFX_ERR_UNSUPPORTED;
+  if (d.Wq < 2 && d.Hq < 64) return VFX_ERR_UNSUPPORTED;            // degenerate grids (UNet centre): SIMT
+  // epilogue vector alignment
+  if (d.out_raw && (d.o_sW % 4 || d.o_sH % 4 || d.o_sB % 4 || d.o_col % 4 || ((uintptr_t)d.out_raw & 15))) return VFX_ERR_UNSUPPORTED;
+  if (d.out_act && (d.oa_sW % 8 || d.oa_sH % 8 || d.oa_sB % 8 || d.oa_col % 8 || ((uintptr_t)d.out_act & 15))) return VFX_ERR_UNSUPPORTED;
+  if (d.residual && (d.r_sW % 4 || d.r_sH % 4 || d.r_sB % 4 || d.r_col % 4 || ((uintptr_t)d.residual & 15))) return VFX_ERR_UNSUPPORTED;
+  if (d.bias && (d.bias_mod % 32 || ((uintptr_t)d.bias & 15))) return VFX_ERR_UNSUPPORTED;
+  for (int t = 0; t < d.ntaps; ++t) if (d.w_off[t] % d.Cin) return VFX_ERR_UNSUPPORTED;
+  EncodeTiledFn encode = get_encode();
+  if (!encode) { set_error("conv_gemm_tc: cuTensorMapEncodeTiled not available"); return VFX_ERR_CUDA; }
+
+  TcParams p;
+  memset(&p, 0, sizeof(p));
+  int tw = 1;
+  while (tw < d.Wq && tw < TILE_M) tw <<= 1;
+  const int th = TILE_M / tw;
+  p.B = d.B; p.Hq = d.Hq; p.Wq = d.Wq; p.tw_log2 = ilog2(tw); p.th = th;
+  p.n_tw = ceil_div(d.Wq, tw); p.n_th = ceil_div(d.Hq, th); p.n_nt = d.N / Ntile; p.Ntile = Ntile;
+  p.KC = KC; p.n_kc = d.Cin / KC; p.ntaps = d.ntaps;
+  p.total_tiles = (long long)d.B * p.n_th * p.n_tw * p.n_nt;
+  long long max_row = 0;
+  for (int t = 0; t < d.ntaps; ++t) {
+    p.dh[t] = d.dh[t]; p.dw[t] = d.dw[t];
+    p.w_row[t] = (int)(d.w_off[t] / d.Cin);
+    if (p.w_row[t] + d.N > max_row) max_row = p.w_row[t] + d.N;
+  }
+  p.sh = d.sh; p.rh = d.rh; p.sw = d.sw; p.rw = d.rw; p.OH = d.OH; p.OW = d.OW; p.N = d.N;
+  p.out_raw = d.out_raw; p.o_sB = d.o_sB; p.o_sH = d.o_sH; p.o_sW = d.o_sW; p.o_col = d.o_col;
+  p.out_act = reinterpret_cast<__nv_bfloat16*>(d.out_act); p.oa_sB = d.oa_sB; p.oa_sH = d.oa_sH; p.oa_sW = d.oa_sW; p.oa_col = d.oa_col;
+  p.bias = d.bias; p.bias_mod = d.bias_mod > 0 ? d.bias_mod : d.N;
+  p.residual = d.residual; p.r_sB = d.r_sB; p.r_sH = d.r_sH; p.r_sW = d.r_sW; p.r_col = d.r_col;
+  p.act = d.act; p.act_param = d.act_param;
+  // instruction descriptor: c=F32 [4,6)=1, a=BF16 [7,10)=1, b=BF16 [10,13)=1, K-major both, N>>3 [17,23), M>>4 [24,29)
+  p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(Ntile >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
+  const uint32_t row_bytes = KC * 2;
+  p.a_stage_bytes = TILE_M * row_bytes;
+  p.b_stage_bytes = Ntile * row_bytes;
+  p.sbo16 = (8 * row_bytes) >> 4;
+  p.layout_type = KC == 64 ? 2u : 4u;
+  p.tmem_cols = 2 * Ntile < 32 ? 32 : 2 * Ntile;
+  const uint32_t stage_bytes = p.a_stage_bytes + p.b_stage_bytes;
+  int stages = (int)((200 * 1024) / stage_bytes);
+  if (stages > 8) stages = 8;
+  const int k_steps = p.ntaps * p.n_kc;
+  if (stages < 2) return VFX_ERR_UNSUPPORTED;
+  p.stages = stages;
+  (void)k_steps;
+  const size_t smem_bytes = (size_t)stages * stage_bytes + 1024 + (2 * stages + 4) * 8 + 16;
+
+  // ---- tensor maps
+  CUtensorMap tmA, tmW;
+  const CUtensorMapSwizzle swz = KC == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+  {
+    cuuint64_t dims[4] = {(cuuint64_t)d.Cin, (cuuint64_t)d.W, (cuuint64_t)d.H, (cuuint64_t)d.B};
+    cuuint64_t strides[3] = {(cuuint64_t)d.a_sW * 2, (cuuint64_t)d.a_sH * 2, (cuuint64_t)d.a_sB * 2};
+    // a degenerate dimension of extent 1 may carry any stride; keep them valid multiples of 16
+    cuuint32_t box[4] = {(cuuint32_t)KC, (cuuint32_t)tw, (cuuint32_t)th, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = encode(&tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(d.a), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("conv_gemm_tc: cuTensorMapEncodeTiled(A) failed with %d", (int)r); return VFX_ERR_CUDA; }
+  }
+  {
+    cuuint64_t dims[2] = {(cuuint64_t)d.Cin, (cuuint64_t)max_row};
+    cuuint64_t strides[1] = {(cuuint64_t)d.Cin * 2};
+    cuuint32_t box[2] = {(cuuint32_t)KC, (cuuint32_t)Ntile};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = encode(&tmW, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(d.w), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("conv_gemm_tc: cuTensorMapEncodeTiled(W) failed with %d", (int)r); return VFX_ERR_CUDA; }
+  }
+
+  static int num_sms = 0;
+  if (!num_sms) {
+    int dev = 0;
+    VFX_CUDA_CHECK(cudaGetDevice(&dev));
+    VFX_CUDA_CHECK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+    VFX_CUDA_CHECK(cudaFuncSetAttribute(conv_gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  }
+  const int grid = (int)(p.total_tiles < num_sms ? p.total_tiles : num_sms);
+  conv_gemm_tc_kernel<<<grid, NUM_THREADS, smem_bytes, st>>>(tmA, tmW, p);
+  VFX_LAUNCH_CHECK();
+  return VFX_OK;
+}
+
+}  // namespace vfx
