@@ -1,0 +1,47 @@
+"""Micro-benchmark of the conv-GEMM kernels on the vocoder ResStack shapes (CUDA events).
+usage: python tools/bench_conv.py [--only C] [--B 8] [--iters 5] [--impl 1]"""
+import argparse, os, sys, ctypes
+import torch
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+from gpu_util import conv_gemm
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--only", type=int, default=0)
+ap.add_argument("--B", type=int, default=8)
+ap.add_argument("--iters", type=int, default=5)
+ap.add_argument("--impl", type=int, default=1)
+ap.add_argument("--kind", default="both")
+args = ap.parse_args()
+dev = "cuda:0"
+shapes = [(512, 7042), (256, 49294), (128, 147882), (64, 443646)]
+for C, L in shapes:
+    if args.only and C != args.only:
+        continue
+    B = args.B
+    a = (torch.randn(B, 1, L, C, device=dev) * 0.5).bfloat16()
+    w = (torch.randn(3, C, C, device=dev) * 0.05).bfloat16()
+    bias = torch.randn(C, device=dev)
+    X = torch.randn(B, 1, L, C, device=dev)
+    out_act = torch.empty(B, 1, L, C, device=dev, dtype=torch.bfloat16)
+    for kind in ("c1", "c2"):
+        if args.kind not in ("both", kind):
+            continue
+        def run():
+            if kind == "c1":
+                conv_gemm(a, w, [(0, -3), (0, 0), (0, 3)], bias=bias, want_raw=False, want_act=True, act="lrelu",
+                          act_param=0.01, precision="bf16", impl=args.impl, out_act=out_act)
+            else:
+                conv_gemm(a, w, [(0, -1), (0, 0), (0, 1)], bias=bias, residual=X, want_raw=True, want_act=True,
+                          act="lrelu", act_param=0.01, precision="bf16", impl=args.impl, out_raw=X, out_act=out_act)
+        run()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.iters):
+            run()
+        e1.record(); torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / args.iters
+        flops = 2.0 * 3 * C * C * L * B
+        byts = B * L * C * (4 if kind == "c1" else 12)
+        print(f"C={C:4d} L={L:7d} B={B} {kind}: {ms:8.3f} ms  {flops/ms/1e9:8.1f} TF/s  {byts/ms/1e6:8.1f} GB/s (algorithmic)", flush=True)

@@ -23,12 +23,11 @@ namespace {
 
 constexpr int TILE_M = 128;
 constexpr int NUM_THREADS = 192;          // 6 warps
-constexpr int EPI_WARP0 = 2;
 
 struct TcParams {
   // tile schedule
   int B, Hq, Wq, tw_log2, th, n_tw, n_th, n_nt, Ntile, KC, n_kc, ntaps, stages;
-  long long total_tiles;
+  uint32_t total_tiles;
   int dh[9], dw[9];
   int w_row[9];             // first weight row of each tap (w_off / Cin)
   // output mapping
@@ -116,18 +115,36 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t sbo1
   return d;
 }
 
+// Compile-time activation for the bf16 operand output (compact code: the generic runtime switch
+// with sinf/expm1f slow paths made the epilogue instruction-fetch bound).  Results are rounded to
+// bf16 (rel. 4e-3), so the fast intrinsics (abs. error ~1e-6 after range reduction) are ample.
+template <int ACT>
+__device__ __forceinline__ float act_fast(float v, float p) {
+  if (ACT == VFX_ACT_LRELU) return v > 0.f ? v : v * p;
+  if (ACT == VFX_ACT_ELU) return v > 0.f ? v : __expf(v) - 1.f;
+  if (ACT == VFX_ACT_LRELU_XSINX) {
+    const float u = v > 0.f ? v : v * p;
+    const float k = rintf(u * 0.15915494309189535f);            // u / 2pi
+    const float r = fmaf(k, -6.2831854820251465f, u);            // Cody-Waite, 2 terms
+    return u + __sinf(fmaf(k, 1.7484555e-7f, r));
+  }
+  if (ACT == VFX_ACT_SIGMOID) return 1.f / (1.f + __expf(-v));
+  return v;
+}
+
 struct TileCoord { int b, h0, w0, n0; };
-__device__ __forceinline__ TileCoord decode_tile(const TcParams& p, long long tile) {
+__device__ __forceinline__ TileCoord decode_tile(const TcParams& p, uint32_t tile) {
   TileCoord t;
-  const int nt = (int)(tile % p.n_nt);
-  long long m = tile / p.n_nt;
-  const int iw = (int)(m % p.n_tw); m /= p.n_tw;
-  const int ih = (int)(m % p.n_th);
-  t.b = (int)(m / p.n_th);
+  const uint32_t nt = tile % (uint32_t)p.n_nt;
+  uint32_t m = tile / (uint32_t)p.n_nt;
+  const uint32_t iw = m % (uint32_t)p.n_tw; m /= (uint32_t)p.n_tw;
+  const uint32_t ih = m % (uint32_t)p.n_th;
+  t.b = (int)(m / (uint32_t)p.n_th);
   t.h0 = ih * p.th; t.w0 = iw << p.tw_log2; t.n0 = nt * p.Ntile;
   return t;
 }
 
+template <int ACT>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
                     const __grid_constant__ TcParams p) {
@@ -165,9 +182,11 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     // ===================== TMA producer =====================
     if (lane == 0) {
       uint32_t s = 0, ph = 0;
-      for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      for (uint32_t tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
         const TileCoord t = decode_tile(p, tile);
+#pragma unroll 1
         for (int tap = 0; tap < p.ntaps; ++tap) {
+#pragma unroll 1
           for (int kc = 0; kc < p.n_kc; ++kc) {
             mbar_wait(&empty[s], ph ^ 1);
             uint8_t* sa = smem + (size_t)s * stage_bytes;
@@ -184,10 +203,11 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     if (lane == 0) {
       uint32_t s = 0, ph = 0, acc = 0, acc_ph = 0;
       const int kk = p.KC / 16;                       // UMMA_K = 16 for bf16
-      for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      for (uint32_t tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
         mbar_wait(&tmem_empty[acc], acc_ph ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * p.Ntile;
+#pragma unroll 1
         for (int ks = 0; ks < k_steps; ++ks) {
           mbar_wait(&full[s], ph);
           tc_fence_after();
@@ -211,14 +231,18 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const int sub = warp & 3;                         // TMEM sub-partition this warp may access
     const int row = sub * 32 + lane;                  // accumulator row = position inside the patch
     uint32_t acc = 0, acc_ph = 0;
-    for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+    for (uint32_t tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
       const TileCoord t = decode_tile(p, tile);
       const int qh = t.h0 + (row >> p.tw_log2), qw = t.w0 + (row & ((1 << p.tw_log2) - 1));
       const int oh = qh * p.sh + p.rh, ow = qw * p.sw + p.rw;
       const bool valid = qh < p.Hq && qw < p.Wq && oh < p.OH && ow < p.OW;
+      const long long off_r = (long long)t.b * p.r_sB + (long long)oh * p.r_sH + (long long)ow * p.r_sW + p.r_col + t.n0;
+      const long long off_o = (long long)t.b * p.o_sB + (long long)oh * p.o_sH + (long long)ow * p.o_sW + p.o_col + t.n0;
+      const long long off_a = (long long)t.b * p.oa_sB + (long long)oh * p.oa_sH + (long long)ow * p.oa_sW + p.oa_col + t.n0;
       mbar_wait(&tmem_full[acc], acc_ph);
       tc_fence_after();
       const uint32_t t_row = tmem_base + ((uint32_t)(sub * 32) << 16) + acc * p.Ntile;
+#pragma unroll 1
       for (int c0 = 0; c0 < p.Ntile; c0 += 32) {
         uint32_t v[32];
         tc_ld32(t_row + c0, v);
@@ -236,8 +260,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             }
           }
           if (p.residual) {
-            const float4* rp = reinterpret_cast<const float4*>(
-                p.residual + (long long)t.b * p.r_sB + (long long)oh * p.r_sH + (long long)ow * p.r_sW + p.r_col + n);
+            const float4* rp = reinterpret_cast<const float4*>(p.residual + off_r + c0);
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
               const float4 r4 = rp[j];
@@ -245,21 +268,19 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             }
           }
           if (p.out_raw) {
-            float4* op = reinterpret_cast<float4*>(
-                p.out_raw + (long long)t.b * p.o_sB + (long long)oh * p.o_sH + (long long)ow * p.o_sW + p.o_col + n);
+            float4* op = reinterpret_cast<float4*>(p.out_raw + off_o + c0);
 #pragma unroll
             for (int j = 0; j < 8; ++j) op[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
           }
           if (p.out_act) {
-            uint4* ap = reinterpret_cast<uint4*>(
-                p.out_act + (long long)t.b * p.oa_sB + (long long)oh * p.oa_sH + (long long)ow * p.oa_sW + p.oa_col + n);
+            uint4* ap = reinterpret_cast<uint4*>(p.out_act + off_a + c0);
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               uint32_t w[4];
 #pragma unroll
               for (int q = 0; q < 4; ++q) {
-                const float lo = apply_act(f[8 * j + 2 * q], p.act, p.act_param);
-                const float hi = apply_act(f[8 * j + 2 * q + 1], p.act, p.act_param);
+                const float lo = act_fast<ACT>(f[8 * j + 2 * q], p.act_param);
+                const float hi = act_fast<ACT>(f[8 * j + 2 * q + 1], p.act_param);
                 __nv_bfloat162 h2 = __floats2bfloat162_rn(lo, hi);
                 w[q] = *reinterpret_cast<uint32_t*>(&h2);
               }
@@ -331,7 +352,9 @@ int conv_gemm_tc(const vfx_conv_desc& d, cudaStream_t st) {
   p.B = d.B; p.Hq = d.Hq; p.Wq = d.Wq; p.tw_log2 = ilog2(tw); p.th = th;
   p.n_tw = ceil_div(d.Wq, tw); p.n_th = ceil_div(d.Hq, th); p.n_nt = d.N / Ntile; p.Ntile = Ntile;
   p.KC = KC; p.n_kc = d.Cin / KC; p.ntaps = d.ntaps;
-  p.total_tiles = (long long)d.B * p.n_th * p.n_tw * p.n_nt;
+  const long long total_tiles = (long long)d.B * p.n_th * p.n_tw * p.n_nt;
+  if (total_tiles >= (1LL << 31)) return VFX_ERR_UNSUPPORTED;
+  p.total_tiles = (uint32_t)total_tiles;
   long long max_row = 0;
   for (int t = 0; t < d.ntaps; ++t) {
     p.dh[t] = d.dh[t]; p.dw[t] = d.dw[t];
@@ -391,10 +414,20 @@ int conv_gemm_tc(const vfx_conv_desc& d, cudaStream_t st) {
     int dev = 0;
     VFX_CUDA_CHECK(cudaGetDevice(&dev));
     VFX_CUDA_CHECK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
-    VFX_CUDA_CHECK(cudaFuncSetAttribute(conv_gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+#define VFX_TC_ATTR(A) VFX_CUDA_CHECK(cudaFuncSetAttribute(conv_gemm_tc_kernel<A>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024))
+    VFX_TC_ATTR(VFX_ACT_NONE); VFX_TC_ATTR(VFX_ACT_LRELU); VFX_TC_ATTR(VFX_ACT_ELU); VFX_TC_ATTR(VFX_ACT_LRELU_XSINX);
+    VFX_TC_ATTR(VFX_ACT_SIGMOID);
+#undef VFX_TC_ATTR
   }
-  const int grid = (int)(p.total_tiles < num_sms ? p.total_tiles : num_sms);
-  conv_gemm_tc_kernel<<<grid, NUM_THREADS, smem_bytes, st>>>(tmA, tmW, p);
+  const int grid = (int)(p.total_tiles < (uint32_t)num_sms ? p.total_tiles : (uint32_t)num_sms);
+  const int act = d.out_act ? d.act : VFX_ACT_NONE;
+  switch (act) {
+#define VFX_TC_LAUNCH(A) case A: conv_gemm_tc_kernel<A><<<grid, NUM_THREADS, smem_bytes, st>>>(tmA, tmW, p); break
+    VFX_TC_LAUNCH(VFX_ACT_NONE); VFX_TC_LAUNCH(VFX_ACT_LRELU); VFX_TC_LAUNCH(VFX_ACT_ELU);
+    VFX_TC_LAUNCH(VFX_ACT_LRELU_XSINX); VFX_TC_LAUNCH(VFX_ACT_SIGMOID);
+#undef VFX_TC_LAUNCH
+    default: set_error("conv_gemm_tc: unknown activation %d", act); return VFX_ERR_INVALID;
+  }
   VFX_LAUNCH_CHECK();
   return VFX_OK;
 }
