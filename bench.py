@@ -80,11 +80,51 @@ def measured_peaks():
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
 
 
+def host_threads():
+    """Usable host threads: affinity mask and cgroup quota, not just os.cpu_count()."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        q, per = open("/sys/fs/cgroup/cpu.max").read().split()
+        if q != "max":
+            n = max(1, min(n, int(float(q) / float(per))))
+    except Exception:
+        pass
+    return n
+
+
+_BEST_THREADS = None
+
+
+def best_cpu_threads():
+    """PyTorch CPU throughput of this path peaks well below a 128-thread box's core count (small
+    GEMMs + a 4000-step GRU loop oversubscribe); calibrate on 0.3 s of audio and keep the fastest."""
+    global _BEST_THREADS
+    if _BEST_THREADS is None:
+        from voicefixer_b200 import synthetic
+        from oracle import vf_oracle as O
+        ana, voc = synthetic.make_analysis_state(0), synthetic.make_vocoder_state(1)
+        wav = synthetic.make_utterances(1, seconds=0.3, seed=5)[0]
+        n = host_threads()
+        best = None
+        for t in sorted({min(n, c) for c in (8, 16, 32, 64, n)}):
+            torch.set_num_threads(t)
+            O.restore_inmem(wav, ana, voc, mode=0)
+            t0 = time.perf_counter()
+            O.restore_inmem(wav, ana, voc, mode=0)
+            dt = time.perf_counter() - t0
+            if best is None or dt < best[0]:
+                best = (dt, t)
+            if dt > 20:
+                break
+        _BEST_THREADS = best[1]
+    return _BEST_THREADS
+
+
 def cpu_reference_rate(seconds, threads=None):
     """The reference's CPU path (oracle port of restore_inmem, PyTorch fp32) on the host cores."""
     from voicefixer_b200 import synthetic
     from oracle import vf_oracle as O
-    threads = threads or os.cpu_count()
+    threads = threads or best_cpu_threads()
     torch.set_num_threads(threads)
     ana, voc = synthetic.make_analysis_state(0), synthetic.make_vocoder_state(1)
     wav = synthetic.make_utterances(1, seconds=seconds, seed=1234)[0]
@@ -134,7 +174,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=32, help="utterances per GPU")
     ap.add_argument("--seconds", type=float, default=10.0)
-    ap.add_argument("--precision", default=os.environ.get("VFX_PRECISION", "fp32"))
+    ap.add_argument("--precision", default=os.environ.get("VFX_PRECISION", "bf16"),
+                    help="bf16 = tcgen05 tensor-core path (default); fp32 = SIMT validation path")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -256,12 +297,14 @@ def main():
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        sample_s = 5.0
-        run, threads = cpu_reference_rate(sample_s)
+        run1, threads = cpu_reference_rate(1.0)
+        t1 = run1()
+        sample_s = float(min(10.0, max(1.0, round(20.0 / max(t1, 1e-3)))))      # ~20 s of CPU work
+        run, threads = cpu_reference_rate(sample_s, threads)
         dt = run()
         cpu_baseline = {"value": sample_s / dt, "unit": UNIT, "cores": threads, "kind": "port",
                         "sample": f"1 x {sample_s:.0f} s utterance, restore_inmem mode 0 (oracle port, PyTorch fp32), "
-                                  f"{dt:.1f} s wall"}
+                                  f"{dt:.1f} s wall, {threads} of {host_threads()} host threads (fastest of a sweep)"}
 
     if rank == 0:
         print(json.dumps({

@@ -130,3 +130,28 @@ def test_frontend_rejects_short_input(engine):
     from voicefixer_b200._lib import VfxError
     with pytest.raises(VfxError, match="1024"):
         engine.frontend(np.zeros((1, 1000), np.float32))
+
+
+def test_hf_cut_mode1_prefilter_vs_oracle(engine):
+    """vfx_hf_cut vs the oracle's restatement of remove_higher_frequency (base.py:87-104)."""
+    from voicefixer_b200 import synthetic
+    from oracle import vf_oracle as O
+    wav = synthetic.make_utterances(2, seconds=0.8, seed=41)
+    out, cut = engine.hf_cut(wav)
+    for b in range(2):
+        ref = O.remove_higher_frequency(wav[b])
+        assert out.shape[1] == ref.shape[0] == 512 * (wav.shape[1] // 512)
+        assert rel_rms(out[b].cpu().numpy(), ref) < 1e-4
+    assert all(0 < int(c) < 1025 for c in cut.cpu())
+
+
+def test_restore_mode1_vs_oracle(engine, states):
+    """mode 1 end to end through the API semantics: pre-filter, shorter output (132300 -> 132096 style)."""
+    from voicefixer_b200 import synthetic
+    from oracle import vf_oracle as O
+    wav = synthetic.make_utterances(1, seconds=0.6, seed=43)[0]
+    ref = O.restore_inmem(wav, states[0], states[1], mode=1)
+    x, _ = engine.hf_cut(wav[None])
+    out = engine.restore(x).cpu().numpy()
+    assert out.shape == ref.shape == (1, 512 * (wav.shape[0] // 512))
+    assert rel_rms(out, ref) < 2e-4

@@ -5,38 +5,11 @@
 // (voicefixer/tools/mel_scale.py:63-77), as called by VoiceFixer._pre voicefixer/base.py:78-85.
 // The unused cos/sin phase outputs are not computed.
 #include "vfx_common.cuh"
+#include "fft.cuh"
 
 namespace vfx {
 
 namespace {
-
-__device__ __forceinline__ float2 cmul(float2 a, float2 b) {
-  return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
-}
-
-// In-place-in-shared-memory complex FFT of 1024 points (radix-2 Stockham autosort, 10 passes,
-// 256 threads, two butterflies per thread per pass).  tw[i] = exp(-2*pi*i*I/2048), i < 1024.
-// Returns the buffer holding the result.
-__device__ float2* fft1024(float2* a, float2* b, const float2* __restrict__ tw, int tid) {
-  float2* src = a; float2* dst = b;
-#pragma unroll 1
-  for (int Ns = 1; Ns < 1024; Ns <<= 1) {
-#pragma unroll
-    for (int q = 0; q < 2; ++q) {
-      const int j = tid + q * 256;          // butterfly index 0..511
-      const int k = j & (Ns - 1);
-      const float2 w = tw[k * (1024 / Ns)];
-      const float2 u = src[j];
-      const float2 v = cmul(w, src[j + 512]);
-      const int j0 = ((j - k) << 1) + k;
-      dst[j0] = make_float2(u.x + v.x, u.y + v.y);
-      dst[j0 + Ns] = make_float2(u.x - v.x, u.y - v.y);
-    }
-    __syncthreads();
-    float2* t = src; src = dst; dst = t;
-  }
-  return src;
-}
 
 __global__ void __launch_bounds__(256) stft_mel_kernel(const float* __restrict__ wav, int L, int T,
                                                        const float* __restrict__ window,
@@ -66,17 +39,8 @@ __global__ void __launch_bounds__(256) stft_mel_kernel(const float* __restrict__
   const float2* Z = fft1024(bufA, bufB, tw, tid);
   // untangle the packed real transform, magnitude with the reference's clamp (eps 1e-8)
   for (int k = tid; k <= 1024; k += 256) {
-    float re, im;
-    if (k == 1024) {
-      re = Z[0].x - Z[0].y; im = 0.f;
-    } else {
-      const float2 zk = Z[k], zn = Z[(1024 - k) & 1023];
-      const float2 e = make_float2(0.5f * (zk.x + zn.x), 0.5f * (zk.y - zn.y));
-      const float2 o = make_float2(0.5f * (zk.y + zn.y), -0.5f * (zk.x - zn.x));   // -i/2 (zk - conj zn)
-      const float2 wo = cmul(tw[k], o);
-      re = e.x + wo.x; im = e.y + wo.y;
-    }
-    const float m = sqrtf(fmaxf(re * re + im * im, 1e-8f));
+    const float2 X = rfft_untangle(Z, tw, k);
+    const float m = sqrtf(fmaxf(X.x * X.x + X.y * X.y, 1e-8f));
     mag[k] = m;
     if (sp) sp[((long long)b * T + t) * 1025 + k] = m;
   }

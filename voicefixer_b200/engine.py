@@ -194,7 +194,8 @@ class Engine:
         B, L = wav.shape
         out = torch.empty(B, 512 * (L // 512), device=wav.device)
         cut = torch.empty(B, dtype=torch.int32, device=wav.device)
-        ws = self._workspace(max(1 << 20, 64 * B * (L + 4096)))
+        nfr = 1 + L // 512
+        ws = self._workspace(B * nfr * (1025 * 8 + 2048 * 4) + B * 1025 * 8 + (1 << 16))
         _lib.check(self.lib.vfx_hf_cut(self.h, _ptr(wav), B, L, float(ratio), _ptr(out), _ptr(cut), _ptr(ws), ws.numel(),
                                        _stream()), "vfx_hf_cut")
         return out, cut
