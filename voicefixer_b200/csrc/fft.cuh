@@ -4,14 +4,14 @@
 
 namespace vfx {
 
-__device__ __forceinline__ float2 cmul(float2 a, float2 b) {
+static __device__ __forceinline__ float2 cmul(float2 a, float2 b) {
   return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
 }
 
 // In-place-in-shared-memory complex FFT of 1024 points (radix-2 Stockham autosort, 10 passes,
 // 256 threads, two butterflies per thread per pass).  tw[i] = exp(-2*pi*i*I/2048), i < 1024.
 // Returns the buffer holding the result.
-__device__ float2* fft1024(float2* a, float2* b, const float2* __restrict__ tw, int tid) {
+static __device__ __forceinline__ float2* fft1024(float2* a, float2* b, const float2* __restrict__ tw, int tid) {
   float2* src = a; float2* dst = b;
 #pragma unroll 1
   for (int Ns = 1; Ns < 1024; Ns <<= 1) {
@@ -35,7 +35,7 @@ __device__ float2* fft1024(float2* a, float2* b, const float2* __restrict__ tw, 
 
 // X[k], k in [0,1024], of the 2048-point real transform whose even/odd samples were packed as
 // z[n] = x[2n] + i x[2n+1] and transformed into Z (1024 complex).  tw[k] = exp(-2 pi i k / 2048).
-__device__ __forceinline__ float2 rfft_untangle(const float2* Z, const float2* __restrict__ tw, int k) {
+static __device__ __forceinline__ float2 rfft_untangle(const float2* Z, const float2* __restrict__ tw, int k) {
   if (k == 1024) return make_float2(Z[0].x - Z[0].y, 0.f);
   const float2 zk = Z[k], zn = Z[(1024 - k) & 1023];
   const float2 e = make_float2(0.5f * (zk.x + zn.x), 0.5f * (zk.y - zn.y));
