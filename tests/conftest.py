@@ -9,6 +9,10 @@ if ROOT not in sys.path:
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 
 
+import torch
+torch.set_num_threads(min(8, os.cpu_count() or 1))   # the CPU oracle oversubscribes a 128-core box
+
+
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
 

@@ -102,6 +102,8 @@ def test_gru_layer_matches_torch_gru():
     from voicefixer_b200 import _lib
     lib = _lib.load()
     B, T = 5, 37
+    torch.backends.cudnn.allow_tf32 = False          # the cuDNN GRU reference would run TF32 otherwise
+    torch.backends.cuda.matmul.allow_tf32 = False
     torch.manual_seed(0)
     gru = torch.nn.GRU(512, 256, num_layers=1, bidirectional=True, batch_first=True).to(_dev())
     x = _rnd(B, T, 512, seed=14)

@@ -11,7 +11,9 @@
 //   zero-filled by TMA, which IS the convolution's zero padding (no im2col, no halo logic).
 // * Persistent CTAs (one per SM), static round-robin tile schedule, warp roles:
 //     warp 0   TMA producer (one elected lane)        warp 1   tcgen05.mma issuer (one lane)
-//     warp 2-5 epilogue: tcgen05.ld TMEM->registers, +bias, +residual(fp32), activation, stores
+//     warp 2-9 epilogue: tcgen05.ld TMEM->registers, +bias, +residual(fp32), activation, stores
+//              (8 warps: sub-partition = warp%4, column chunks split even/odd between the pair;
+//               residual rows are prefetched before the accumulator wait and one chunk ahead)
 //   smem ring of S stages (full/empty mbarriers) and 2 TMEM accumulator stages (tmem_full/empty)
 //   so the epilogue of tile i overlaps the MMAs of tile i+1.
 #include <cuda.h>
@@ -22,7 +24,8 @@ namespace vfx {
 namespace {
 
 constexpr int TILE_M = 128;
-constexpr int NUM_THREADS = 192;          // 6 warps
+constexpr int NUM_EPI_WARPS = 8;          // two per TMEM sub-partition, interleaved over column chunks
+constexpr int NUM_THREADS = 64 + 32 * NUM_EPI_WARPS;
 
 struct TcParams {
   // tile schedule
@@ -42,6 +45,8 @@ struct TcParams {
   uint32_t sbo16;           // stride-byte-offset >> 4 of the K-major swizzled layout (8 rows)
   uint32_t layout_type;     // 2 = SWIZZLE_128B, 4 = SWIZZLE_64B
   uint32_t tmem_cols;
+  uint32_t w_resident;      // all taps' weights stay in smem for the CTA's lifetime (single N tile)
+  uint32_t w_bytes;         // bytes of the resident weight region (0 if streamed)
 };
 
 // ------------------------------------------------------------------ PTX wrappers
@@ -150,13 +155,17 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     const __grid_constant__ TcParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  const uint32_t stage_bytes = p.a_stage_bytes + p.b_stage_bytes;
+  // [resident weights | S stages of (A [+ W])] | barriers
+  uint8_t* wres = smem;
+  smem += p.w_bytes;
+  const uint32_t stage_bytes = p.a_stage_bytes + (p.w_resident ? 0u : p.b_stage_bytes);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * stage_bytes);
   uint64_t* full = bars;
   uint64_t* empty = bars + p.stages;
   uint64_t* tmem_full = bars + 2 * p.stages;
   uint64_t* tmem_empty = tmem_full + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  uint64_t* wfull = tmem_empty + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wfull + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -164,7 +173,8 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmW)) : "memory");
     for (int s = 0; s < p.stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], 128); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], 32 * NUM_EPI_WARPS); }
+    mbar_init(wfull, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {   // TMEM allocation (whole warp), address published through smem
@@ -181,6 +191,14 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
+      if (p.w_resident) {       // every tap's [N][Cin] matrix once, as [tap][kc] blocks of [Ntile][KC]
+        mbar_expect_tx(wfull, p.w_bytes);
+#pragma unroll 1
+        for (int tap = 0; tap < p.ntaps; ++tap)
+#pragma unroll 1
+          for (int kc = 0; kc < p.n_kc; ++kc)
+            tma_load_2d(&tmW, wfull, wres + (size_t)(tap * p.n_kc + kc) * p.b_stage_bytes, kc * p.KC, p.w_row[tap]);
+      }
       uint32_t s = 0, ph = 0;
       for (uint32_t tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
         const TileCoord t = decode_tile(p, tile);
@@ -192,7 +210,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             uint8_t* sa = smem + (size_t)s * stage_bytes;
             mbar_expect_tx(&full[s], stage_bytes);
             tma_load_4d(&tmA, &full[s], sa, kc * p.KC, t.w0 + p.dw[tap], t.h0 + p.dh[tap], t.b);
-            tma_load_2d(&tmW, &full[s], sa + p.a_stage_bytes, kc * p.KC, p.w_row[tap] + t.n0);
+            if (!p.w_resident) tma_load_2d(&tmW, &full[s], sa + p.a_stage_bytes, kc * p.KC, p.w_row[tap] + t.n0);
             if (++s == (uint32_t)p.stages) { s = 0; ph ^= 1; }
           }
         }
@@ -203,6 +221,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     if (lane == 0) {
       uint32_t s = 0, ph = 0, acc = 0, acc_ph = 0;
       const int kk = p.KC / 16;                       // UMMA_K = 16 for bf16
+      if (p.w_resident) { mbar_wait(wfull, 0); tc_fence_after(); }
       for (uint32_t tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
         mbar_wait(&tmem_empty[acc], acc_ph ^ 1);
         tc_fence_after();
@@ -212,7 +231,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           mbar_wait(&full[s], ph);
           tc_fence_after();
           const uint32_t a_addr = smem_u32(smem + (size_t)s * stage_bytes);
-          const uint32_t b_addr = a_addr + p.a_stage_bytes;
+          const uint32_t b_addr = p.w_resident ? smem_u32(wres + (size_t)ks * p.b_stage_bytes) : a_addr + p.a_stage_bytes;
 #pragma unroll 4
           for (int k = 0; k < kk; ++k) {
             const uint64_t ad = make_smem_desc(a_addr + k * 32, p.sbo16, p.layout_type);
@@ -227,8 +246,9 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       }
     }
   } else {
-    // ===================== epilogue (4 warps = 128 TMEM lanes) =====================
+    // ===================== epilogue (8 warps over 128 TMEM lanes) =====================
     const int sub = warp & 3;                         // TMEM sub-partition this warp may access
+    const int half = (warp - 2) >> 2;                 // 0/1: which column chunks (even/odd) this warp takes
     const int row = sub * 32 + lane;                  // accumulator row = position inside the patch
     uint32_t acc = 0, acc_ph = 0;
     for (uint32_t tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
@@ -239,13 +259,29 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       const long long off_r = (long long)t.b * p.r_sB + (long long)oh * p.r_sH + (long long)ow * p.r_sW + p.r_col + t.n0;
       const long long off_o = (long long)t.b * p.o_sB + (long long)oh * p.o_sH + (long long)ow * p.o_sW + p.o_col + t.n0;
       const long long off_a = (long long)t.b * p.oa_sB + (long long)oh * p.oa_sH + (long long)ow * p.oa_sW + p.oa_col + t.n0;
+      const bool has_res = p.residual != nullptr && valid;
+      // residual of this warp's first chunk: in flight while the MMAs of the tile finish
+      float4 rcur[8];
+      int c0 = half * 32;
+      if (has_res && c0 < p.Ntile) {
+        const float4* rp = reinterpret_cast<const float4*>(p.residual + off_r + c0);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) rcur[j] = __ldcs(rp + j);
+      }
       mbar_wait(&tmem_full[acc], acc_ph);
       tc_fence_after();
       const uint32_t t_row = tmem_base + ((uint32_t)(sub * 32) << 16) + acc * p.Ntile;
 #pragma unroll 1
-      for (int c0 = 0; c0 < p.Ntile; c0 += 32) {
+      for (; c0 < p.Ntile; c0 += 64) {
         uint32_t v[32];
         tc_ld32(t_row + c0, v);
+        float4 rnext[8];
+        const bool more = has_res && (c0 + 64 < p.Ntile);
+        if (more) {                                   // next chunk's residual: in flight during this chunk
+          const float4* rp = reinterpret_cast<const float4*>(p.residual + off_r + c0 + 64);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) rnext[j] = __ldcs(rp + j);
+        }
         if (valid) {
           const int n = t.n0 + c0;
           float f[32];
@@ -259,12 +295,10 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
               f[4 * j] += b4.x; f[4 * j + 1] += b4.y; f[4 * j + 2] += b4.z; f[4 * j + 3] += b4.w;
             }
           }
-          if (p.residual) {
-            const float4* rp = reinterpret_cast<const float4*>(p.residual + off_r + c0);
+          if (has_res) {
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-              const float4 r4 = rp[j];
-              f[4 * j] += r4.x; f[4 * j + 1] += r4.y; f[4 * j + 2] += r4.z; f[4 * j + 3] += r4.w;
+              f[4 * j] += rcur[j].x; f[4 * j + 1] += rcur[j].y; f[4 * j + 2] += rcur[j].z; f[4 * j + 3] += rcur[j].w;
             }
           }
           if (p.out_raw) {
@@ -287,6 +321,10 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
               ap[j] = make_uint4(w[0], w[1], w[2], w[3]);
             }
           }
+        }
+        if (more) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) rcur[j] = rnext[j];
         }
       }
       tc_fence_before();
@@ -375,14 +413,17 @@ int conv_gemm_tc(const vfx_conv_desc& d, cudaStream_t st) {
   p.sbo16 = (8 * row_bytes) >> 4;
   p.layout_type = KC == 64 ? 2u : 4u;
   p.tmem_cols = 2 * Ntile < 32 ? 32 : 2 * Ntile;
-  const uint32_t stage_bytes = p.a_stage_bytes + p.b_stage_bytes;
-  int stages = (int)((200 * 1024) / stage_bytes);
+  const size_t w_all = (size_t)p.ntaps * p.n_kc * p.b_stage_bytes;
+  p.w_resident = (p.n_nt == 1 && w_all <= 100 * 1024) ? 1u : 0u;
+  p.w_bytes = p.w_resident ? (uint32_t)w_all : 0u;
+  const uint32_t stage_bytes = p.a_stage_bytes + (p.w_resident ? 0u : p.b_stage_bytes);
+  int stages = (int)((200 * 1024 - p.w_bytes) / stage_bytes);
   if (stages > 8) stages = 8;
   const int k_steps = p.ntaps * p.n_kc;
   if (stages < 2) return VFX_ERR_UNSUPPORTED;
   p.stages = stages;
   (void)k_steps;
-  const size_t smem_bytes = (size_t)stages * stage_bytes + 1024 + (2 * stages + 4) * 8 + 16;
+  const size_t smem_bytes = (size_t)p.w_bytes + (size_t)stages * stage_bytes + 1024 + (2 * stages + 5) * 8 + 16;
 
   // ---- tensor maps
   CUtensorMap tmA, tmW;
