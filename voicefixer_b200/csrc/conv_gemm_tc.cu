@@ -14,9 +14,11 @@
 //     warp 2-9 epilogue: tcgen05.ld TMEM->registers, +bias, +residual(fp32), activation, stores
 //              (8 warps: sub-partition = warp%4, column chunks split even/odd between the pair;
 //               residual rows are prefetched before the accumulator wait and one chunk ahead)
-//   smem ring of S stages (full/empty mbarriers) and 2 TMEM accumulator stages (tmem_full/empty)
-//   so the epilogue of tile i overlaps the MMAs of tile i+1.
+//   smem ring of S stages (full/empty mbarriers) and up to 8 TMEM accumulator stages (512 columns /
+//   Ntile; tmem_full/empty) so the MMA -> epilogue -> MMA latency chain is pipelined several tiles deep.
 #include <cuda.h>
+#include <stdlib.h>
+#include <vector>
 #include "vfx_common.cuh"
 
 namespace vfx {
@@ -26,6 +28,7 @@ namespace {
 constexpr int TILE_M = 128;
 constexpr int NUM_EPI_WARPS = 8;          // two per TMEM sub-partition, interleaved over column chunks
 constexpr int NUM_THREADS = 64 + 32 * NUM_EPI_WARPS;
+constexpr int BIAS_SMEM_FLOATS = 1024;                   // TMA epilogue keeps bias[0..bias_mod) in smem
 
 struct TcParams {
   // tile schedule
@@ -47,6 +50,13 @@ struct TcParams {
   uint32_t tmem_cols;
   uint32_t w_resident;      // all taps' weights stay in smem for the CTA's lifetime (single N tile)
   uint32_t w_bytes;         // bytes of the resident weight region (0 if streamed)
+  uint32_t tma_epi;         // plain (stride-1) conv: residual in / raw+operand out through TMA-staged tiles
+  uint32_t epi_arrivals;    // threads arriving on tmem_empty
+  uint32_t epi_warp_bytes, epi_at_off;   // TMA epilogue: per-warp staging bytes, offset of the bf16 tiles
+  uint32_t nacc;            // TMEM accumulator stages (2..8): depth of the MMA <-> epilogue pipeline
+  uint32_t jtiles;          // tiles whose k-steps are interleaved (independent accumulators hide MMA latency)
+  long long* dbg;           // optional per-CTA role counters (VFX_TC_DEBUG)
+  int bw_log2;              // TMA epilogue: a warp's 32 rows form a (32/bw) x bw sub-patch, bw = min(tw, 32)
 };
 
 // ------------------------------------------------------------------ PTX wrappers
@@ -70,6 +80,9 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       "bra WAIT_LOOP;\n\t"
       "WAIT_DONE:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
 }
+__device__ __forceinline__ void mbar_wait_t(uint64_t* bar, uint32_t parity, long long& acc, bool on) {
+  if (on) { const long long t0 = clock64(); mbar_wait(bar, parity); acc += clock64() - t0; } else mbar_wait(bar, parity);
+}
 __device__ __forceinline__ void tma_load_4d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1, int c2, int c3) {
   asm volatile(
       "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
@@ -81,6 +94,17 @@ __device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* ba
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
       ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
       : "memory");
+}
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, const void* src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+// one elected lane of a fully converged warp (keeps the surrounding control flow and all operands
+// warp-uniform, so descriptors/coordinates stay in uniform registers instead of R2UR waterfalls)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -152,20 +176,24 @@ __device__ __forceinline__ TileCoord decode_tile(const TcParams& p, uint32_t til
 template <int ACT>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
-                    const __grid_constant__ TcParams p) {
+                    const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CUtensorMap tmO,
+                    const __grid_constant__ CUtensorMap tmT, const __grid_constant__ TcParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  // [resident weights | S stages of (A [+ W])] | barriers
+  // [resident weights | S stages of (A [+ W]) | epilogue staging (TMA epilogue) | barriers]
   uint8_t* wres = smem;
   smem += p.w_bytes;
   const uint32_t stage_bytes = p.a_stage_bytes + (p.w_resident ? 0u : p.b_stage_bytes);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * stage_bytes);
+  uint8_t* staging = smem + (size_t)p.stages * stage_bytes;
+  float* bias_s = reinterpret_cast<float*>(staging + (p.tma_epi ? NUM_EPI_WARPS * p.epi_warp_bytes : 0));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(bias_s + (p.tma_epi ? BIAS_SMEM_FLOATS : 0));
   uint64_t* full = bars;
   uint64_t* empty = bars + p.stages;
   uint64_t* tmem_full = bars + 2 * p.stages;
-  uint64_t* tmem_empty = tmem_full + 2;
-  uint64_t* wfull = tmem_empty + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wfull + 1);
+  uint64_t* tmem_empty = tmem_full + 8;
+  uint64_t* wfull = tmem_empty + 8;
+  uint64_t* res_full = wfull + 1;                       // [8 warps][2 buffers]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_full + 16);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -173,14 +201,17 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmW)) : "memory");
     for (int s = 0; s < p.stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], 32 * NUM_EPI_WARPS); }
+    for (int a = 0; a < 8; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], p.epi_arrivals); }
     mbar_init(wfull, 1);
+    for (int i = 0; i < 16; ++i) mbar_init(&res_full[i], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {   // TMEM allocation (whole warp), address published through smem
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(p.tmem_cols) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
+  if (p.tma_epi)
+    for (int i = threadIdx.x; i < p.bias_mod; i += NUM_THREADS) bias_s[i] = p.bias ? p.bias[i] : 0.f;
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -189,9 +220,9 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   const int k_steps = p.ntaps * p.n_kc;
 
   if (warp == 0) {
-    // ===================== TMA producer =====================
-    if (lane == 0) {
-      if (p.w_resident) {       // every tap's [N][Cin] matrix once, as [tap][kc] blocks of [Ntile][KC]
+    // ===================== TMA producer (warp-uniform loop, one elected lane issues) =====================
+    {
+      if (p.w_resident && elect_one()) {   // every tap's [N][Cin] matrix once, as [tap][kc] blocks of [Ntile][KC]
         mbar_expect_tx(wfull, p.w_bytes);
 #pragma unroll 1
         for (int tap = 0; tap < p.ntaps; ++tap)
@@ -199,51 +230,195 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           for (int kc = 0; kc < p.n_kc; ++kc)
             tma_load_2d(&tmW, wfull, wres + (size_t)(tap * p.n_kc + kc) * p.b_stage_bytes, kc * p.KC, p.w_row[tap]);
       }
+      __syncwarp();
       uint32_t s = 0, ph = 0;
-      for (uint32_t tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-        const TileCoord t = decode_tile(p, tile);
+      const bool dbg = p.dbg != nullptr;
+      long long w_empty = 0; const long long tstart = dbg ? clock64() : 0;
+      // tiles of this CTA: tile(i) = blockIdx.x + i * gridDim.x; groups of J tiles advance through their
+      // k-steps together: (tile 0, ks 0), (tile 1, ks 0), ..., (tile 0, ks 1), ...
+      const uint32_t n_my = blockIdx.x < p.total_tiles ? (p.total_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+      for (uint32_t i0 = 0; i0 < n_my; i0 += p.jtiles) {
+        const uint32_t jn = (n_my - i0) < p.jtiles ? (n_my - i0) : p.jtiles;
+        TileCoord tc[4];
+#pragma unroll
+        for (uint32_t j = 0; j < 4; ++j) tc[j] = decode_tile(p, blockIdx.x + (i0 + (j < jn ? j : 0)) * gridDim.x);
 #pragma unroll 1
         for (int tap = 0; tap < p.ntaps; ++tap) {
 #pragma unroll 1
           for (int kc = 0; kc < p.n_kc; ++kc) {
-            mbar_wait(&empty[s], ph ^ 1);
-            uint8_t* sa = smem + (size_t)s * stage_bytes;
-            mbar_expect_tx(&full[s], stage_bytes);
-            tma_load_4d(&tmA, &full[s], sa, kc * p.KC, t.w0 + p.dw[tap], t.h0 + p.dh[tap], t.b);
-            if (!p.w_resident) tma_load_2d(&tmW, &full[s], sa + p.a_stage_bytes, kc * p.KC, p.w_row[tap] + t.n0);
+#pragma unroll
+            for (uint32_t j = 0; j < 4; ++j) {
+              if (j < jn) {
+                mbar_wait_t(&empty[s], ph ^ 1, w_empty, dbg);
+                uint8_t* sa = smem + (size_t)s * stage_bytes;
+                if (elect_one()) {
+                  mbar_expect_tx(&full[s], stage_bytes);
+                  tma_load_4d(&tmA, &full[s], sa, kc * p.KC, tc[j].w0 + p.dw[tap], tc[j].h0 + p.dh[tap], tc[j].b);
+                  if (!p.w_resident) tma_load_2d(&tmW, &full[s], sa + p.a_stage_bytes, kc * p.KC, p.w_row[tap] + tc[j].n0);
+                }
+                __syncwarp();
+                if (++s == (uint32_t)p.stages) { s = 0; ph ^= 1; }
+              }
+            }
+          }
+        }
+      }
+      if (dbg && lane == 0) { long long* o = p.dbg + (long long)blockIdx.x * 64; o[0] = clock64() - tstart; o[1] = w_empty; }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (warp-uniform loop, one elected lane issues) =====================
+    {
+      uint32_t s = 0, ph = 0;
+      const int kk = p.KC / 16;                       // UMMA_K = 16 for bf16
+      if (p.w_resident) { mbar_wait(wfull, 0); tc_fence_after(); }
+      const bool dbg = p.dbg != nullptr;
+      long long w_full = 0, w_te = 0, w_mma = 0, w_cm = 0, w_cm2 = 0; const long long tstart = dbg ? clock64() : 0;
+      const uint32_t n_my = blockIdx.x < p.total_tiles ? (p.total_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+      const uint32_t nacc_mask = p.nacc - 1, nacc_log2 = 31 - __clz(p.nacc);
+      for (uint32_t i0 = 0; i0 < n_my; i0 += p.jtiles) {
+        const uint32_t jn = (n_my - i0) < p.jtiles ? (n_my - i0) : p.jtiles;
+        for (uint32_t j = 0; j < jn; ++j) {            // accumulators of the whole group must be drained
+          const uint32_t i = i0 + j;
+          mbar_wait_t(&tmem_empty[i & nacc_mask], ((i >> nacc_log2) & 1) ^ 1, w_te, dbg);
+        }
+        tc_fence_after();
+#pragma unroll 1
+        for (int ks = 0; ks < k_steps; ++ks) {
+          for (uint32_t j = 0; j < jn; ++j) {
+            const uint32_t d_tmem = tmem_base + ((i0 + j) & nacc_mask) * p.Ntile;
+            mbar_wait_t(&full[s], ph, w_full, dbg);
+            tc_fence_after();
+            const uint32_t a_addr = smem_u32(smem + (size_t)s * stage_bytes);
+            const uint32_t b_addr = p.w_resident ? smem_u32(wres + (size_t)ks * p.b_stage_bytes) : a_addr + p.a_stage_bytes;
+            const long long tm0 = dbg ? clock64() : 0;
+            if (elect_one()) {
+#pragma unroll 4
+              for (int k = 0; k < kk; ++k) {
+                const uint64_t ad = make_smem_desc(a_addr + k * 32, p.sbo16, p.layout_type);
+                const uint64_t bd = make_smem_desc(b_addr + k * 32, p.sbo16, p.layout_type);
+                tc_mma_bf16(d_tmem, ad, bd, p.idesc, (ks | k) ? 1u : 0u);
+              }
+              tc_commit(&empty[s]);                   // frees the smem stage when these MMAs retire
+              if (ks == k_steps - 1) tc_commit(&tmem_full[(i0 + j) & nacc_mask]);   // accumulator ready for the epilogue
+            }
+            __syncwarp();
+            if (dbg) w_mma += clock64() - tm0;
             if (++s == (uint32_t)p.stages) { s = 0; ph ^= 1; }
           }
         }
       }
+      if (dbg && lane == 0) { long long* o = p.dbg + (long long)blockIdx.x * 64 + 8; o[0] = clock64() - tstart; o[1] = w_full; o[2] = w_te; o[3] = w_mma; o[4] = w_cm; o[5] = w_cm2; }
     }
-  } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
-      uint32_t s = 0, ph = 0, acc = 0, acc_ph = 0;
-      const int kk = p.KC / 16;                       // UMMA_K = 16 for bf16
-      if (p.w_resident) { mbar_wait(wfull, 0); tc_fence_after(); }
-      for (uint32_t tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-        mbar_wait(&tmem_empty[acc], acc_ph ^ 1);
-        tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * p.Ntile;
+  } else if (p.tma_epi) {
+    // ===================== TMA-staged epilogue (8 warps; plain stride-1 convs) =====================
+    // Warp (sub = warp%4, half = (warp-2)/4) owns accumulator rows [32 sub, 32 sub + 32) = a (32/bw) x bw
+    // sub-patch and the 32-column chunks c = half, half+2, ...  Per chunk: the fp32 residual tile arrives
+    // by TMA (prefetched one chunk ahead, across tiles) in a SWIZZLE_128B staging tile; the thread owning
+    // a row reads its 128 B, adds accumulator + bias (smem copy), writes the fp32 result back IN PLACE and
+    // the activated bf16 operand into a SWIZZLE_64B tile; one lane issues the TMA stores (full lines,
+    // asynchronous, rows/columns outside the tensor are clipped by the tensor map).
+    const int ew = warp - 2, sub = warp & 3, half = ew >> 2;
+    uint8_t* const stg = staging + ew * p.epi_warp_bytes;      // [RO0 RO1 (4 KB each, optional)] [AT0 AT1 (2 KB each)]
+    uint8_t* const at_base = stg + p.epi_at_off;
+    uint64_t* const rfull = res_full + ew * 2;
+    const bool has_res = p.residual != nullptr;
+    const int r0 = sub * 32;
+    const int dh0 = r0 >> p.tw_log2, dw0 = r0 & ((1 << p.tw_log2) - 1);
+    const int nch = p.Ntile >> 5;
+    uint32_t k = 0, rph = 0, acc = 0, acc_ph = 0;               // rph bit b = phase of rfull[b]
+    if (has_res && lane == 0 && blockIdx.x < p.total_tiles && half < nch) {
+      const TileCoord t = decode_tile(p, blockIdx.x);
+      mbar_expect_tx(&rfull[0], 4096);
+      tma_load_4d(&tmR, &rfull[0], stg, p.r_col + t.n0 + half * 32, t.w0 + dw0, t.h0 + dh0, t.b);
+    }
+    const uint32_t sw128 = (uint32_t)(lane & 7) << 4, sw64 = (uint32_t)((lane >> 1) & 3) << 4;
+    const bool dbg = p.dbg != nullptr;
+    long long w_tf = 0, w_rf = 0, w_wg = 0, w_ld = 0; const long long tstart = dbg ? clock64() : 0;
+    for (uint32_t tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      const TileCoord t = decode_tile(p, tile);
+      uint32_t bcol = ((uint32_t)t.n0 + half * 32) % (uint32_t)p.bias_mod;
+      mbar_wait_t(&tmem_full[acc], acc_ph, w_tf, dbg);
+      tc_fence_after();
+      const uint32_t t_row = tmem_base + ((uint32_t)(sub * 32) << 16) + acc * p.Ntile;
 #pragma unroll 1
-        for (int ks = 0; ks < k_steps; ++ks) {
-          mbar_wait(&full[s], ph);
-          tc_fence_after();
-          const uint32_t a_addr = smem_u32(smem + (size_t)s * stage_bytes);
-          const uint32_t b_addr = p.w_resident ? smem_u32(wres + (size_t)ks * p.b_stage_bytes) : a_addr + p.a_stage_bytes;
-#pragma unroll 4
-          for (int k = 0; k < kk; ++k) {
-            const uint64_t ad = make_smem_desc(a_addr + k * 32, p.sbo16, p.layout_type);
-            const uint64_t bd = make_smem_desc(b_addr + k * 32, p.sbo16, p.layout_type);
-            tc_mma_bf16(d_tmem, ad, bd, p.idesc, (ks | k) ? 1u : 0u);
+      for (int c = half; c < nch; c += 2) {
+        const int col = t.n0 + c * 32;
+        uint8_t* const ro = stg + k * 4096 + lane * 128;
+        if (has_res) { mbar_wait_t(&rfull[k], (rph >> k) & 1, w_rf, dbg); rph ^= 1u << k; }
+        uint32_t v[32];
+        { const long long t0 = dbg ? clock64() : 0; tc_ld32(t_row + c * 32, v); if (dbg) w_ld += clock64() - t0; }
+        float f[32];
+        {
+          const float4* bp = reinterpret_cast<const float4*>(bias_s + bcol);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 b4 = bp[j];
+            f[4 * j] = __uint_as_float(v[4 * j]) + b4.x; f[4 * j + 1] = __uint_as_float(v[4 * j + 1]) + b4.y;
+            f[4 * j + 2] = __uint_as_float(v[4 * j + 2]) + b4.z; f[4 * j + 3] = __uint_as_float(v[4 * j + 3]) + b4.w;
           }
-          tc_commit(&empty[s]);                       // frees the smem stage when these MMAs retire
-          if (++s == (uint32_t)p.stages) { s = 0; ph ^= 1; }
         }
-        tc_commit(&tmem_full[acc]);                   // accumulator ready for the epilogue
-        if (++acc == 2) { acc = 0; acc_ph ^= 1; }
+        bcol += 64; while (bcol >= (uint32_t)p.bias_mod) bcol -= (uint32_t)p.bias_mod;
+        if (has_res) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 r4 = *reinterpret_cast<const float4*>(ro + ((uint32_t)(j << 4) ^ sw128));
+            f[4 * j] += r4.x; f[4 * j + 1] += r4.y; f[4 * j + 2] += r4.z; f[4 * j + 3] += r4.w;
+          }
+        }
+        if (p.out_raw) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            *reinterpret_cast<float4*>(ro + ((uint32_t)(j << 4) ^ sw128)) = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+        }
+        if (p.out_act) {
+          uint8_t* const at = at_base + k * 2048 + lane * 64;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            uint32_t w[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const float lo = act_fast<ACT>(f[8 * j + 2 * q], p.act_param);
+              const float hi = act_fast<ACT>(f[8 * j + 2 * q + 1], p.act_param);
+              __nv_bfloat162 h2 = __floats2bfloat162_rn(lo, hi);
+              w[q] = *reinterpret_cast<uint32_t*>(&h2);
+            }
+            *reinterpret_cast<uint4*>(at + ((uint32_t)(j << 4) ^ sw64)) = make_uint4(w[0], w[1], w[2], w[3]);
+          }
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) {
+          if (p.out_raw) tma_store_4d(&tmO, stg + k * 4096, p.o_col + col, t.w0 + dw0, t.h0 + dh0, t.b);
+          if (p.out_act) tma_store_4d(&tmT, at_base + k * 2048, p.oa_col + col, t.w0 + dw0, t.h0 + dh0, t.b);
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          { const long long t0 = dbg ? clock64() : 0;
+            asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");   // buffers k^1 are free again
+            if (dbg) w_wg += clock64() - t0; }
+          if (has_res) {          // residual of this warp's next chunk (this tile or the next one) -> buffer k^1
+            TileCoord tn = t; int cn = c + 2; bool more = true;
+            if (cn >= nch) {
+              cn = half;
+              const uint32_t nt = tile + gridDim.x;
+              more = nt < p.total_tiles;
+              if (more) tn = decode_tile(p, nt);
+            }
+            if (more) {
+              mbar_expect_tx(&rfull[k ^ 1], 4096);
+              tma_load_4d(&tmR, &rfull[k ^ 1], stg + (k ^ 1) * 4096, p.r_col + tn.n0 + cn * 32, tn.w0 + dw0, tn.h0 + dh0, tn.b);
+            }
+          }
+        }
+        __syncwarp();
+        k ^= 1;
       }
+      tc_fence_before();
+      mbar_arrive(&tmem_empty[acc]);
+      if (++acc == p.nacc) { acc = 0; acc_ph ^= 1; }
+    }
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    if (dbg && lane == 0) {
+      long long* o = p.dbg + (long long)blockIdx.x * 64 + 16 + ew * 6;
+      o[0] = clock64() - tstart; o[1] = w_tf; o[2] = w_rf; o[3] = w_wg; o[4] = w_ld;
     }
   } else {
     // ===================== epilogue (8 warps over 128 TMEM lanes) =====================
@@ -329,7 +504,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       }
       tc_fence_before();
       mbar_arrive(&tmem_empty[acc]);
-      if (++acc == 2) { acc = 0; acc_ph ^= 1; }
+      if (++acc == p.nacc) { acc = 0; acc_ph ^= 1; }
     }
   }
 
@@ -412,18 +587,34 @@ int conv_gemm_tc(const vfx_conv_desc& d, cudaStream_t st) {
   p.b_stage_bytes = Ntile * row_bytes;
   p.sbo16 = (8 * row_bytes) >> 4;
   p.layout_type = KC == 64 ? 2u : 4u;
-  p.tmem_cols = 2 * Ntile < 32 ? 32 : 2 * Ntile;
+  p.nacc = 512 / Ntile > 8 ? 8 : 512 / Ntile;        // Ntile 256 -> 2, 128 -> 4, <= 64 -> 8
+  p.tmem_cols = 32;
+  while (p.tmem_cols < p.nacc * Ntile) p.tmem_cols <<= 1;
+  static const int jt_env = getenv("VFX_TC_JTILES") ? atoi(getenv("VFX_TC_JTILES")) : 0;
+  p.jtiles = 1u;    // interleaving tiles did not help once the issue path was made warp-uniform (kept as a knob)
+  if (jt_env >= 1 && jt_env <= 4 && (uint32_t)jt_env * 2 <= p.nacc) p.jtiles = (uint32_t)jt_env;
   const size_t w_all = (size_t)p.ntaps * p.n_kc * p.b_stage_bytes;
   p.w_resident = (p.n_nt == 1 && w_all <= 100 * 1024) ? 1u : 0u;
   p.w_bytes = p.w_resident ? (uint32_t)w_all : 0u;
+  // plain stride-1 convolution whose output grid is the tensor itself -> TMA-staged epilogue
+  static const bool allow_tma_epi = getenv("VFX_NO_TMA_EPI") == nullptr;
+  p.tma_epi = (allow_tma_epi && d.sh == 1 && d.sw == 1 && d.rh == 0 && d.rw == 0 && d.OH == d.Hq && d.OW == d.Wq) ? 1u : 0u;
+  if (p.tma_epi && p.bias_mod > BIAS_SMEM_FLOATS) p.tma_epi = 0;
+  p.epi_arrivals = 32u * NUM_EPI_WARPS;
+  const bool needs_ro = d.out_raw || d.residual;
+  p.epi_at_off = needs_ro ? 8192u : 0u;
+  p.epi_warp_bytes = p.epi_at_off + (d.out_act ? 4096u : 0u);
+  const uint32_t epi_smem = p.tma_epi ? NUM_EPI_WARPS * p.epi_warp_bytes + BIAS_SMEM_FLOATS * 4 : 0u;
+  if (p.w_resident && p.w_bytes + epi_smem + 3 * p.a_stage_bytes > 200 * 1024) { p.w_resident = 0; p.w_bytes = 0; }
+  p.bw_log2 = p.tw_log2 < 5 ? p.tw_log2 : 5;
   const uint32_t stage_bytes = p.a_stage_bytes + (p.w_resident ? 0u : p.b_stage_bytes);
-  int stages = (int)((200 * 1024 - p.w_bytes) / stage_bytes);
+  int stages = (int)((200 * 1024 - p.w_bytes - epi_smem) / stage_bytes);
   if (stages > 8) stages = 8;
   const int k_steps = p.ntaps * p.n_kc;
   if (stages < 2) return VFX_ERR_UNSUPPORTED;
   p.stages = stages;
   (void)k_steps;
-  const size_t smem_bytes = (size_t)p.w_bytes + (size_t)stages * stage_bytes + 1024 + (2 * stages + 5) * 8 + 16;
+  const size_t smem_bytes = (size_t)p.w_bytes + (size_t)stages * stage_bytes + epi_smem + 1024 + (2 * stages + 17 + 16) * 8 + 16;
 
   // ---- tensor maps
   CUtensorMap tmA, tmW;
@@ -450,6 +641,31 @@ int conv_gemm_tc(const vfx_conv_desc& d, cudaStream_t st) {
     if (r != CUDA_SUCCESS) { set_error("conv_gemm_tc: cuTensorMapEncodeTiled(W) failed with %d", (int)r); return VFX_ERR_CUDA; }
   }
 
+  CUtensorMap tmR = tmA, tmO = tmA, tmT = tmA;     // placeholders when the direct epilogue is used
+  if (p.tma_epi) {
+    const cuuint32_t bw = 1u << p.bw_log2, bh = 32u >> p.bw_log2;
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    auto enc = [&](CUtensorMap* tm, CUtensorMapDataType dt, int esz, const void* base, long long cols, long long sW, long long sH,
+                   long long sB, CUtensorMapSwizzle swz) -> CUresult {
+      cuuint64_t dims[4] = {(cuuint64_t)cols, (cuuint64_t)d.OW, (cuuint64_t)d.OH, (cuuint64_t)d.B};
+      cuuint64_t strides[3] = {(cuuint64_t)sW * esz, (cuuint64_t)sH * esz, (cuuint64_t)sB * esz};
+      cuuint32_t box[4] = {32, bw, bh, 1};
+      return encode(tm, dt, 4, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
+                    CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    };
+    CUresult r = CUDA_SUCCESS;
+    if (d.residual) r = enc(&tmR, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, d.residual, d.r_col + d.N, d.r_sW, d.r_sH, d.r_sB, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (r == CUDA_SUCCESS && d.out_raw) r = enc(&tmO, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, d.out_raw, d.o_col + d.N, d.o_sW, d.o_sH, d.o_sB, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (r == CUDA_SUCCESS && d.out_act) r = enc(&tmT, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, d.out_act, d.oa_col + d.N, d.oa_sW, d.oa_sH, d.oa_sB, CU_TENSOR_MAP_SWIZZLE_64B);
+    if (r != CUDA_SUCCESS) { set_error("conv_gemm_tc: cuTensorMapEncodeTiled(epilogue) failed with %d", (int)r); return VFX_ERR_CUDA; }
+  }
+
+  static long long* dbg_buf = nullptr;
+  static const bool want_dbg = getenv("VFX_TC_DEBUG") != nullptr;
+  if (want_dbg && !dbg_buf) { VFX_CUDA_CHECK(cudaMalloc(&dbg_buf, 148 * 64 * sizeof(long long))); }
+  if (want_dbg) VFX_CUDA_CHECK(cudaMemsetAsync(dbg_buf, 0, 148 * 64 * sizeof(long long), st));
+  p.dbg = want_dbg ? dbg_buf : nullptr;
+
   static int num_sms = 0;
   if (!num_sms) {
     int dev = 0;
@@ -463,13 +679,26 @@ int conv_gemm_tc(const vfx_conv_desc& d, cudaStream_t st) {
   const int grid = (int)(p.total_tiles < (uint32_t)num_sms ? p.total_tiles : (uint32_t)num_sms);
   const int act = d.out_act ? d.act : VFX_ACT_NONE;
   switch (act) {
-#define VFX_TC_LAUNCH(A) case A: conv_gemm_tc_kernel<A><<<grid, NUM_THREADS, smem_bytes, st>>>(tmA, tmW, p); break
+#define VFX_TC_LAUNCH(A) case A: conv_gemm_tc_kernel<A><<<grid, NUM_THREADS, smem_bytes, st>>>(tmA, tmW, tmR, tmO, tmT, p); break
     VFX_TC_LAUNCH(VFX_ACT_NONE); VFX_TC_LAUNCH(VFX_ACT_LRELU); VFX_TC_LAUNCH(VFX_ACT_ELU);
     VFX_TC_LAUNCH(VFX_ACT_LRELU_XSINX); VFX_TC_LAUNCH(VFX_ACT_SIGMOID);
 #undef VFX_TC_LAUNCH
     default: set_error("conv_gemm_tc: unknown activation %d", act); return VFX_ERR_INVALID;
   }
   VFX_LAUNCH_CHECK();
+  if (want_dbg) {
+    std::vector<long long> h(148 * 64);
+    VFX_CUDA_CHECK(cudaMemcpyAsync(h.data(), dbg_buf, h.size() * sizeof(long long), cudaMemcpyDeviceToHost, st));
+    VFX_CUDA_CHECK(cudaStreamSynchronize(st));
+    for (int cta : {0, 73, 147}) {
+      const long long* o = h.data() + cta * 64;
+      fprintf(stderr, "[tc dbg] cta %3d tiles/cta %u | producer total %lld wait_empty %lld | mma total %lld wait_full %lld wait_tmem_empty %lld issue4mma %lld commit_stage %lld commit_acc %lld\n",
+              cta, (p.total_tiles + grid - 1) / grid, o[0], o[1], o[8], o[9], o[10], o[11], o[12], o[13]);
+      for (int w = 0; w < 8; w += 4)
+        fprintf(stderr, "[tc dbg]   epi warp %d: total %lld wait_tmem_full %lld wait_res %lld wait_store_group %lld tmem_ld %lld\n", w,
+                o[16 + w * 6], o[17 + w * 6], o[18 + w * 6], o[19 + w * 6], o[20 + w * 6]);
+    }
+  }
   return VFX_OK;
 }
 
