@@ -54,6 +54,9 @@ struct TcParams {
   uint32_t epi_arrivals;    // threads arriving on tmem_empty
   uint32_t epi_warp_bytes, epi_at_off;   // TMA epilogue: per-warp staging bytes, offset of the bf16 tiles
   uint32_t nacc;            // TMEM accumulator stages (2..8): depth of the MMA <-> epilogue pipeline
+  int d_nt, d_iw, d_ih, d_b; // mixed-radix digits of gridDim.x in (n_nt, n_tw, n_th, B): per-iteration tile increment
+  uint32_t halo;            // 1-D conv, taps (-d,0,+d), d <= 64: ONE (128+2d)-row box per tile, taps = row-shifted views
+  uint32_t halo_d, halo_rows, halo_kc_bytes;
   uint32_t jtiles;          // tiles whose k-steps are interleaved (independent accumulators hide MMA latency)
   long long* dbg;           // optional per-CTA role counters (VFX_TC_DEBUG)
   int bw_log2;              // TMA epilogue: a warp's 32 rows form a (32/bw) x bw sub-patch, bw = min(tw, 32)
@@ -143,6 +146,9 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t sbo1
   d |= (uint64_t)(layout_type & 7) << 61;
   return d;
 }
+// Row-shifted views of a SWIZZLE_128B tile (halo mode) use the same descriptor with the shifted start
+// address and base_offset 0: verified on B200 that the MMA unit, like TMA, derives the swizzle phase
+// from the absolute shared-memory address bits [7,10) (base_offset = (addr>>7)&7 gives wrong results).
 
 // Compile-time activation for the bf16 operand output (compact code: the generic runtime switch
 // with sinf/expm1f slow paths made the epilogue instruction-fetch bound).  Results are rounded to
@@ -164,6 +170,11 @@ __device__ __forceinline__ float act_fast(float v, float p) {
 struct TileCoord { int b, h0, w0, n0; };
 __device__ __forceinline__ TileCoord decode_tile(const TcParams& p, uint32_t tile) {
   TileCoord t;
+  if (p.n_nt == 1 && p.n_th == 1) {       // 1-D convolution, one N tile: a single division
+    const uint32_t b = tile / (uint32_t)p.n_tw;
+    t.b = (int)b; t.h0 = 0; t.w0 = (int)((tile - b * (uint32_t)p.n_tw) << p.tw_log2); t.n0 = 0;
+    return t;
+  }
   const uint32_t nt = tile % (uint32_t)p.n_nt;
   uint32_t m = tile / (uint32_t)p.n_nt;
   const uint32_t iw = m % (uint32_t)p.n_tw; m /= (uint32_t)p.n_tw;
@@ -172,6 +183,29 @@ __device__ __forceinline__ TileCoord decode_tile(const TcParams& p, uint32_t til
   t.h0 = ih * p.th; t.w0 = iw << p.tw_log2; t.n0 = nt * p.Ntile;
   return t;
 }
+
+// Tile iterator of a persistent CTA: tile(i) = blockIdx.x + i * gridDim.x.  One real decode (integer
+// divisions are ~250-cycle dependent chains in a lone warp) and then carry-propagating digit adds.
+struct TileIter {
+  int b, ih, iw, nt;
+  __device__ __forceinline__ void init(const TcParams& p, uint32_t tile) {
+    nt = (int)(tile % (uint32_t)p.n_nt);
+    uint32_t m = tile / (uint32_t)p.n_nt;
+    iw = (int)(m % (uint32_t)p.n_tw); m /= (uint32_t)p.n_tw;
+    ih = (int)(m % (uint32_t)p.n_th);
+    b = (int)(m / (uint32_t)p.n_th);
+  }
+  __device__ __forceinline__ void next(const TcParams& p) {
+    nt += p.d_nt; int c = nt >= p.n_nt; nt -= c ? p.n_nt : 0;
+    iw += p.d_iw + c; c = iw >= p.n_tw; iw -= c ? p.n_tw : 0;
+    ih += p.d_ih + c; c = ih >= p.n_th; ih -= c ? p.n_th : 0;
+    b += p.d_b + c;
+  }
+  __device__ __forceinline__ bool valid(const TcParams& p) const { return b < p.B; }
+  __device__ __forceinline__ TileCoord coord(const TcParams& p) const {
+    TileCoord t; t.b = b; t.h0 = ih * p.th; t.w0 = iw << p.tw_log2; t.n0 = nt * p.Ntile; return t;
+  }
+};
 
 template <int ACT>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
@@ -183,7 +217,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   // [resident weights | S stages of (A [+ W]) | epilogue staging (TMA epilogue) | barriers]
   uint8_t* wres = smem;
   smem += p.w_bytes;
-  const uint32_t stage_bytes = p.a_stage_bytes + (p.w_resident ? 0u : p.b_stage_bytes);
+  const uint32_t stage_bytes = p.halo ? p.halo_kc_bytes * (uint32_t)p.n_kc : p.a_stage_bytes + (p.w_resident ? 0u : p.b_stage_bytes);
   uint8_t* staging = smem + (size_t)p.stages * stage_bytes;
   float* bias_s = reinterpret_cast<float*>(staging + (p.tma_epi ? NUM_EPI_WARPS * p.epi_warp_bytes : 0));
   uint64_t* bars = reinterpret_cast<uint64_t*>(bias_s + (p.tma_epi ? BIAS_SMEM_FLOATS : 0));
@@ -237,11 +271,33 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       // tiles of this CTA: tile(i) = blockIdx.x + i * gridDim.x; groups of J tiles advance through their
       // k-steps together: (tile 0, ks 0), (tile 1, ks 0), ..., (tile 0, ks 1), ...
       const uint32_t n_my = blockIdx.x < p.total_tiles ? (p.total_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
-      for (uint32_t i0 = 0; i0 < n_my; i0 += p.jtiles) {
+      uint32_t n_done = 0;
+      TileIter pit; pit.init(p, blockIdx.x);
+      if (p.halo) {
+        for (uint32_t i = 0; i < n_my; ++i) {
+          const TileCoord t = pit.coord(p);
+          pit.next(p);
+          mbar_wait_t(&empty[s], ph ^ 1, w_empty, dbg);
+          uint8_t* sa = smem + (size_t)s * stage_bytes;
+          if (elect_one()) {
+            mbar_expect_tx(&full[s], p.halo_rows * 128u * (uint32_t)p.n_kc);
+#pragma unroll 1
+            for (int kc = 0; kc < p.n_kc; ++kc)
+              tma_load_4d(&tmA, &full[s], sa + (size_t)kc * p.halo_kc_bytes, kc * 64, t.w0 - (int)p.halo_d, 0, t.b);
+          }
+          __syncwarp();
+          if (++s == (uint32_t)p.stages) { s = 0; ph ^= 1; }
+        }
+        n_done = n_my;
+      }
+      for (uint32_t i0 = n_done; i0 < n_my; i0 += p.jtiles) {
         const uint32_t jn = (n_my - i0) < p.jtiles ? (n_my - i0) : p.jtiles;
         TileCoord tc[4];
 #pragma unroll
-        for (uint32_t j = 0; j < 4; ++j) tc[j] = decode_tile(p, blockIdx.x + (i0 + (j < jn ? j : 0)) * gridDim.x);
+        for (uint32_t j = 0; j < 4; ++j) {
+          tc[j] = pit.coord(p);
+          if (j < jn) pit.next(p);
+        }
 #pragma unroll 1
         for (int tap = 0; tap < p.ntaps; ++tap) {
 #pragma unroll 1
@@ -275,7 +331,39 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       long long w_full = 0, w_te = 0, w_mma = 0, w_cm = 0, w_cm2 = 0; const long long tstart = dbg ? clock64() : 0;
       const uint32_t n_my = blockIdx.x < p.total_tiles ? (p.total_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
       const uint32_t nacc_mask = p.nacc - 1, nacc_log2 = 31 - __clz(p.nacc);
-      for (uint32_t i0 = 0; i0 < n_my; i0 += p.jtiles) {
+      uint32_t n_done = 0;
+      if (p.halo) {
+        for (uint32_t i = 0; i < n_my; ++i) {
+          mbar_wait_t(&tmem_empty[i & nacc_mask], ((i >> nacc_log2) & 1) ^ 1, w_te, dbg);
+          mbar_wait_t(&full[s], ph, w_full, dbg);
+          tc_fence_after();
+          const uint32_t d_tmem = tmem_base + (i & nacc_mask) * p.Ntile;
+          const uint32_t s_addr = smem_u32(smem + (size_t)s * stage_bytes);
+          const uint32_t w_addr = smem_u32(wres);
+          if (elect_one()) {
+#pragma unroll 1
+            for (int tap = 0; tap < 3; ++tap) {
+#pragma unroll 1
+              for (int kc = 0; kc < p.n_kc; ++kc) {
+                const uint32_t a_addr = s_addr + (uint32_t)kc * p.halo_kc_bytes + (uint32_t)tap * p.halo_d * 128u;
+                const uint32_t b_addr = w_addr + (uint32_t)(tap * p.n_kc + kc) * p.b_stage_bytes;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                  const uint64_t ad = make_smem_desc(a_addr + k * 32, p.sbo16, p.layout_type);
+                  const uint64_t bd = make_smem_desc(b_addr + k * 32, p.sbo16, p.layout_type);
+                  tc_mma_bf16(d_tmem, ad, bd, p.idesc, (tap | kc | k) ? 1u : 0u);
+                }
+              }
+            }
+            tc_commit(&empty[s]);
+            tc_commit(&tmem_full[i & nacc_mask]);
+          }
+          __syncwarp();
+          if (++s == (uint32_t)p.stages) { s = 0; ph ^= 1; }
+        }
+        n_done = n_my;
+      }
+      for (uint32_t i0 = n_done; i0 < n_my; i0 += p.jtiles) {
         const uint32_t jn = (n_my - i0) < p.jtiles ? (n_my - i0) : p.jtiles;
         for (uint32_t j = 0; j < jn; ++j) {            // accumulators of the whole group must be drained
           const uint32_t i = i0 + j;
@@ -326,17 +414,21 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const int dh0 = r0 >> p.tw_log2, dw0 = r0 & ((1 << p.tw_log2) - 1);
     const int nch = p.Ntile >> 5;
     uint32_t k = 0, rph = 0, acc = 0, acc_ph = 0;               // rph bit b = phase of rfull[b]
+    TileIter eit; eit.init(p, blockIdx.x);
     if (has_res && lane == 0 && blockIdx.x < p.total_tiles && half < nch) {
-      const TileCoord t = decode_tile(p, blockIdx.x);
+      const TileCoord t = eit.coord(p);
       mbar_expect_tx(&rfull[0], 4096);
       tma_load_4d(&tmR, &rfull[0], stg, p.r_col + t.n0 + half * 32, t.w0 + dw0, t.h0 + dh0, t.b);
     }
     const uint32_t sw128 = (uint32_t)(lane & 7) << 4, sw64 = (uint32_t)((lane >> 1) & 3) << 4;
     const bool dbg = p.dbg != nullptr;
-    long long w_tf = 0, w_rf = 0, w_wg = 0, w_ld = 0; const long long tstart = dbg ? clock64() : 0;
+    long long w_tf = 0, w_rf = 0, w_wg = 0, w_ld = 0, w_math = 0, w_fence = 0, w_issue = 0, w_dec = 0; const long long tstart = dbg ? clock64() : 0;
     for (uint32_t tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-      const TileCoord t = decode_tile(p, tile);
-      uint32_t bcol = ((uint32_t)t.n0 + half * 32) % (uint32_t)p.bias_mod;
+      const long long td0 = dbg ? clock64() : 0;
+      const TileCoord t = eit.coord(p);
+      eit.next(p);                                      // eit now points at this CTA's next tile
+      uint32_t bcol = (uint32_t)t.n0 + half * 32;       // plain convs: bias_mod >= N, no modulo
+      if (dbg) w_dec += clock64() - td0;
       mbar_wait_t(&tmem_full[acc], acc_ph, w_tf, dbg);
       tc_fence_after();
       const uint32_t t_row = tmem_base + ((uint32_t)(sub * 32) << 16) + acc * p.Ntile;
@@ -347,6 +439,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         if (has_res) { mbar_wait_t(&rfull[k], (rph >> k) & 1, w_rf, dbg); rph ^= 1u << k; }
         uint32_t v[32];
         { const long long t0 = dbg ? clock64() : 0; tc_ld32(t_row + c * 32, v); if (dbg) w_ld += clock64() - t0; }
+        const long long tq0 = dbg ? clock64() : 0;
         float f[32];
         {
           const float4* bp = reinterpret_cast<const float4*>(bias_s + bcol);
@@ -357,7 +450,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             f[4 * j + 2] = __uint_as_float(v[4 * j + 2]) + b4.z; f[4 * j + 3] = __uint_as_float(v[4 * j + 3]) + b4.w;
           }
         }
-        bcol += 64; while (bcol >= (uint32_t)p.bias_mod) bcol -= (uint32_t)p.bias_mod;
+        bcol += 64;
         if (has_res) {
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
@@ -385,8 +478,11 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             *reinterpret_cast<uint4*>(at + ((uint32_t)(j << 4) ^ sw64)) = make_uint4(w[0], w[1], w[2], w[3]);
           }
         }
+        const long long tq1 = dbg ? clock64() : 0;
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncwarp();
+        const long long tq2 = dbg ? clock64() : 0;
+        if (dbg) { w_math += tq1 - tq0; w_fence += tq2 - tq1; }
         if (lane == 0) {
           if (p.out_raw) tma_store_4d(&tmO, stg + k * 4096, p.o_col + col, t.w0 + dw0, t.h0 + dh0, t.b);
           if (p.out_act) tma_store_4d(&tmT, at_base + k * 2048, p.oa_col + col, t.w0 + dw0, t.h0 + dh0, t.b);
@@ -398,9 +494,8 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             TileCoord tn = t; int cn = c + 2; bool more = true;
             if (cn >= nch) {
               cn = half;
-              const uint32_t nt = tile + gridDim.x;
-              more = nt < p.total_tiles;
-              if (more) tn = decode_tile(p, nt);
+              more = eit.valid(p);                      // eit already points at this CTA's next tile
+              if (more) tn = eit.coord(p);
             }
             if (more) {
               mbar_expect_tx(&rfull[k ^ 1], 4096);
@@ -409,6 +504,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           }
         }
         __syncwarp();
+        if (dbg) w_issue += clock64() - tq2;
         k ^= 1;
       }
       tc_fence_before();
@@ -419,6 +515,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     if (dbg && lane == 0) {
       long long* o = p.dbg + (long long)blockIdx.x * 64 + 16 + ew * 6;
       o[0] = clock64() - tstart; o[1] = w_tf; o[2] = w_rf; o[3] = w_wg; o[4] = w_ld;
+      if (ew == 0) { long long* q = p.dbg + (long long)blockIdx.x * 64 + 56; q[0] = w_math; q[1] = w_fence; q[2] = w_issue; q[3] = w_dec; }
     }
   } else {
     // ===================== epilogue (8 warps over 128 TMEM lanes) =====================
@@ -426,8 +523,10 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const int half = (warp - 2) >> 2;                 // 0/1: which column chunks (even/odd) this warp takes
     const int row = sub * 32 + lane;                  // accumulator row = position inside the patch
     uint32_t acc = 0, acc_ph = 0;
+    TileIter dit; dit.init(p, blockIdx.x);
     for (uint32_t tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-      const TileCoord t = decode_tile(p, tile);
+      const TileCoord t = dit.coord(p);
+      dit.next(p);
       const int qh = t.h0 + (row >> p.tw_log2), qw = t.w0 + (row & ((1 << p.tw_log2) - 1));
       const int oh = qh * p.sh + p.rh, ow = qw * p.sw + p.rw;
       const bool valid = qh < p.Hq && qw < p.Wq && oh < p.OH && ow < p.OW;
@@ -599,7 +698,7 @@ int conv_gemm_tc(const vfx_conv_desc& d, cudaStream_t st) {
   // plain stride-1 convolution whose output grid is the tensor itself -> TMA-staged epilogue
   static const bool allow_tma_epi = getenv("VFX_NO_TMA_EPI") == nullptr;
   p.tma_epi = (allow_tma_epi && d.sh == 1 && d.sw == 1 && d.rh == 0 && d.rw == 0 && d.OH == d.Hq && d.OW == d.Wq) ? 1u : 0u;
-  if (p.tma_epi && p.bias_mod > BIAS_SMEM_FLOATS) p.tma_epi = 0;
+  if (p.tma_epi && (p.bias_mod > BIAS_SMEM_FLOATS || p.bias_mod < d.N)) p.tma_epi = 0;
   p.epi_arrivals = 32u * NUM_EPI_WARPS;
   const bool needs_ro = d.out_raw || d.residual;
   p.epi_at_off = needs_ro ? 8192u : 0u;
@@ -607,7 +706,17 @@ int conv_gemm_tc(const vfx_conv_desc& d, cudaStream_t st) {
   const uint32_t epi_smem = p.tma_epi ? NUM_EPI_WARPS * p.epi_warp_bytes + BIAS_SMEM_FLOATS * 4 : 0u;
   if (p.w_resident && p.w_bytes + epi_smem + 3 * p.a_stage_bytes > 200 * 1024) { p.w_resident = 0; p.w_bytes = 0; }
   p.bw_log2 = p.tw_log2 < 5 ? p.tw_log2 : 5;
-  const uint32_t stage_bytes = p.a_stage_bytes + (p.w_resident ? 0u : p.b_stage_bytes);
+  // halo mode: 1-D conv with taps (-d, 0, +d), d <= 64, resident weights, 128-byte rows
+  static const bool allow_halo = getenv("VFX_NO_HALO") == nullptr;
+  p.halo = 0;
+  if (allow_halo && KC == 64 && d.H == 1 && d.Hq == 1 && d.ntaps == 3 && p.w_resident && tw == TILE_M && d.dw[1] == 0 &&
+      d.dw[2] > 0 && d.dw[2] <= 64 && d.dw[0] == -d.dw[2] && d.dh[0] == 0 && d.dh[1] == 0 && d.dh[2] == 0) {
+    p.halo = 1;
+    p.halo_d = (uint32_t)d.dw[2];
+    p.halo_rows = TILE_M + 2 * p.halo_d;
+    p.halo_kc_bytes = ((p.halo_rows + 7) / 8) * 8 * 128;
+  }
+  const uint32_t stage_bytes = p.halo ? p.halo_kc_bytes * (uint32_t)p.n_kc : p.a_stage_bytes + (p.w_resident ? 0u : p.b_stage_bytes);
   int stages = (int)((200 * 1024 - p.w_bytes - epi_smem) / stage_bytes);
   if (stages > 8) stages = 8;
   const int k_steps = p.ntaps * p.n_kc;
@@ -623,7 +732,7 @@ int conv_gemm_tc(const vfx_conv_desc& d, cudaStream_t st) {
     cuuint64_t dims[4] = {(cuuint64_t)d.Cin, (cuuint64_t)d.W, (cuuint64_t)d.H, (cuuint64_t)d.B};
     cuuint64_t strides[3] = {(cuuint64_t)d.a_sW * 2, (cuuint64_t)d.a_sH * 2, (cuuint64_t)d.a_sB * 2};
     // a degenerate dimension of extent 1 may carry any stride; keep them valid multiples of 16
-    cuuint32_t box[4] = {(cuuint32_t)KC, (cuuint32_t)tw, (cuuint32_t)th, 1};
+    cuuint32_t box[4] = {(cuuint32_t)KC, (cuuint32_t)(p.halo ? p.halo_rows : (uint32_t)tw), (cuuint32_t)th, 1};
     cuuint32_t estr[4] = {1, 1, 1, 1};
     CUresult r = encode(&tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(d.a), dims, strides, box, estr,
                         CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -677,6 +786,13 @@ int conv_gemm_tc(const vfx_conv_desc& d, cudaStream_t st) {
 #undef VFX_TC_ATTR
   }
   const int grid = (int)(p.total_tiles < (uint32_t)num_sms ? p.total_tiles : (uint32_t)num_sms);
+  {
+    uint32_t g = (uint32_t)grid;
+    p.d_nt = (int)(g % (uint32_t)p.n_nt); g /= (uint32_t)p.n_nt;
+    p.d_iw = (int)(g % (uint32_t)p.n_tw); g /= (uint32_t)p.n_tw;
+    p.d_ih = (int)(g % (uint32_t)p.n_th); g /= (uint32_t)p.n_th;
+    p.d_b = (int)g;
+  }
   const int act = d.out_act ? d.act : VFX_ACT_NONE;
   switch (act) {
 #define VFX_TC_LAUNCH(A) case A: conv_gemm_tc_kernel<A><<<grid, NUM_THREADS, smem_bytes, st>>>(tmA, tmW, tmR, tmO, tmT, p); break
@@ -694,6 +810,7 @@ int conv_gemm_tc(const vfx_conv_desc& d, cudaStream_t st) {
       const long long* o = h.data() + cta * 64;
       fprintf(stderr, "[tc dbg] cta %3d tiles/cta %u | producer total %lld wait_empty %lld | mma total %lld wait_full %lld wait_tmem_empty %lld issue4mma %lld commit_stage %lld commit_acc %lld\n",
               cta, (p.total_tiles + grid - 1) / grid, o[0], o[1], o[8], o[9], o[10], o[11], o[12], o[13]);
+      fprintf(stderr, "[tc dbg]   epi warp 0 breakdown: math+sts %lld fence+syncwarp %lld issue(store,commit,wait,prefetch) %lld decode %lld\n", o[56], o[57], o[58], o[59]);
       for (int w = 0; w < 8; w += 4)
         fprintf(stderr, "[tc dbg]   epi warp %d: total %lld wait_tmem_full %lld wait_res %lld wait_store_group %lld tmem_ld %lld\n", w,
                 o[16 + w * 6], o[17 + w * 6], o[18 + w * 6], o[19 + w * 6], o[20 + w * 6]);
