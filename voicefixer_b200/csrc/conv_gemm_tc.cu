@@ -28,7 +28,9 @@ namespace {
 constexpr int TILE_M = 128;
 constexpr int NUM_EPI_WARPS = 8;          // two per TMEM sub-partition, interleaved over column chunks
 constexpr int NUM_THREADS = 64 + 32 * NUM_EPI_WARPS;
-constexpr int BIAS_SMEM_FLOATS = 1024;                   // TMA epilogue keeps bias[0..bias_mod) in smem
+constexpr int SMEM_BUDGET = 216 * 1024;                   // weights + stages + epilogue staging (227 KB max incl. barriers/alignment)
+constexpr int MAX_STAGES = 24;
+constexpr int BIAS_SMEM_FLOATS = 2048;                   // TMA epilogue keeps bias[0..bias_mod) in smem
 
 struct TcParams {
   // tile schedule
@@ -168,22 +170,6 @@ __device__ __forceinline__ float act_fast(float v, float p) {
 }
 
 struct TileCoord { int b, h0, w0, n0; };
-__device__ __forceinline__ TileCoord decode_tile(const TcParams& p, uint32_t tile) {
-  TileCoord t;
-  if (p.n_nt == 1 && p.n_th == 1) {       // 1-D convolution, one N tile: a single division
-    const uint32_t b = tile / (uint32_t)p.n_tw;
-    t.b = (int)b; t.h0 = 0; t.w0 = (int)((tile - b * (uint32_t)p.n_tw) << p.tw_log2); t.n0 = 0;
-    return t;
-  }
-  const uint32_t nt = tile % (uint32_t)p.n_nt;
-  uint32_t m = tile / (uint32_t)p.n_nt;
-  const uint32_t iw = m % (uint32_t)p.n_tw; m /= (uint32_t)p.n_tw;
-  const uint32_t ih = m % (uint32_t)p.n_th;
-  t.b = (int)(m / (uint32_t)p.n_th);
-  t.h0 = ih * p.th; t.w0 = iw << p.tw_log2; t.n0 = nt * p.Ntile;
-  return t;
-}
-
 // Tile iterator of a persistent CTA: tile(i) = blockIdx.x + i * gridDim.x.  One real decode (integer
 // divisions are ~250-cycle dependent chains in a lone warp) and then carry-propagating digit adds.
 struct TileIter {
@@ -704,21 +690,22 @@ int conv_gemm_tc(const vfx_conv_desc& d, cudaStream_t st) {
   p.epi_at_off = needs_ro ? 8192u : 0u;
   p.epi_warp_bytes = p.epi_at_off + (d.out_act ? 4096u : 0u);
   const uint32_t epi_smem = p.tma_epi ? NUM_EPI_WARPS * p.epi_warp_bytes + BIAS_SMEM_FLOATS * 4 : 0u;
-  if (p.w_resident && p.w_bytes + epi_smem + 3 * p.a_stage_bytes > 200 * 1024) { p.w_resident = 0; p.w_bytes = 0; }
+  if (p.w_resident && p.w_bytes + epi_smem + 3 * p.a_stage_bytes > SMEM_BUDGET) { p.w_resident = 0; p.w_bytes = 0; }
   p.bw_log2 = p.tw_log2 < 5 ? p.tw_log2 : 5;
   // halo mode: 1-D conv with taps (-d, 0, +d), d <= 64, resident weights, 128-byte rows
   static const bool allow_halo = getenv("VFX_NO_HALO") == nullptr;
   p.halo = 0;
   if (allow_halo && KC == 64 && d.H == 1 && d.Hq == 1 && d.ntaps == 3 && p.w_resident && tw == TILE_M && d.dw[1] == 0 &&
       d.dw[2] > 0 && d.dw[2] <= 64 && d.dw[0] == -d.dw[2] && d.dh[0] == 0 && d.dh[1] == 0 && d.dh[2] == 0) {
-    p.halo = 1;
     p.halo_d = (uint32_t)d.dw[2];
     p.halo_rows = TILE_M + 2 * p.halo_d;
     p.halo_kc_bytes = ((p.halo_rows + 7) / 8) * 8 * 128;
+    // worth it only if at least 3 tiles can be in flight
+    p.halo = ((uint32_t)SMEM_BUDGET - p.w_bytes - epi_smem) / (p.halo_kc_bytes * (uint32_t)p.n_kc) >= 2 ? 1u : 0u;
   }
   const uint32_t stage_bytes = p.halo ? p.halo_kc_bytes * (uint32_t)p.n_kc : p.a_stage_bytes + (p.w_resident ? 0u : p.b_stage_bytes);
-  int stages = (int)((200 * 1024 - p.w_bytes - epi_smem) / stage_bytes);
-  if (stages > 8) stages = 8;
+  int stages = (int)((SMEM_BUDGET - p.w_bytes - epi_smem) / stage_bytes);
+  if (stages > MAX_STAGES) stages = MAX_STAGES;
   const int k_steps = p.ntaps * p.n_kc;
   if (stages < 2) return VFX_ERR_UNSUPPORTED;
   p.stages = stages;

@@ -315,65 +315,82 @@ int unet_forward(Ctx& c, const float* unet_in, int B, int Tp, float** feat_out) 
 // ------------------------------------------------------------------ denoiser
 // nn.Sequential voicefixer/restorer/model.py:69-99 (always fp32 SIMT: 1 % of the path's FLOPs,
 // recurrent part is precision-sensitive).  mel [B][T][128] -> lin15 raw [B*T][128].
+// Denoiser GEMMs: fp32 SIMT in fp32 mode; in bf16 mode the same tcgen05 kernel as the convolutions
+// (bf16 operands, fp32 accumulate / bias / outputs).  The GRU recurrence itself is always fp32.
 int linear(Ctx& c, const void* a, long long M, int K, const std::string& p, int N, float* out_raw,
-           void* out_act, int act) {
-  vfx_conv_desc d = conv_base(a, 1, 1, (int)M, K, getf(c, p + ".w", (size_t)N * K), N);
+           void* out_act, int act, const char* tag = "dn.linear") {
+  const int prec = c.prec();
+  vfx_conv_desc d = conv_base(a, 1, 1, (int)M, K, getw(c, p + ".w", (size_t)N * K, prec), N);
   d.ntaps = 1;
   d.bias = getf(c, p + ".b", N);
   if (out_raw) set_raw(d, out_raw, N, 0);
   if (out_act) set_act(d, out_act, N, 0, act, 0.f);
-  if (c.dry) return c.rc;
-  if (c.rc != VFX_OK) return c.rc;
-  ProfScope ps(c, "dn.linear", conv_flops(d), 0.0);
-  return conv_gemm_simt(VFX_PREC_FP32, d, c.st);
+  return run_conv(c, prec, d, tag);
 }
 
-int bn_gru(Ctx& c, const std::string& p, const float* x, int B, int T, float* op, float* gi,
+// fp32 tensor -> dense GEMM operand: the tensor itself in fp32 mode, a bf16 copy in bf16 mode
+const void* dn_operand(Ctx& c, const float* x, long long M, int C, void* scratch, int* rc) {
+  *rc = VFX_OK;
+  if (c.prec() == VFX_PREC_FP32) return x;
+  if (!c.dry) *rc = bn_act(c.prec(), x, M * C, C, 1, M, C, nullptr, nullptr, 1, 0, VFX_ACT_NONE, 0.f, scratch, M * C, C, c.st);
+  return scratch;
+}
+
+int bn_gru(Ctx& c, const std::string& p, const float* x, int B, int T, void* op, float* gi,
            float* y0, float* y1) {
   const long long M = (long long)B * T;
+  const int prec = c.prec();
   // BN2d(1) over the (T,512) plane of each item
-  VFX_TRY(bn_act_op(c, VFX_PREC_FP32, p + ".bn", 1, x, (long long)T * 512, 512, B, T, 512, VFX_ACT_NONE, 0.f, op));
-  const float* in = op;
+  VFX_TRY(bn_act_op(c, prec, p + ".bn", 1, x, (long long)T * 512, 512, B, T, 512, VFX_ACT_NONE, 0.f, op));
+  const void* in = op;
   float* outs[2] = {y0, y1};
   for (int layer = 0; layer < 2; ++layer) {
     char nm[64];
     snprintf(nm, sizeof(nm), "%s.l%d", p.c_str(), layer);
     const std::string q(nm);
-    vfx_conv_desc d = conv_base(in, 1, 1, (int)M, 512, getf(c, q + ".wih", (size_t)1536 * 512), 1536);
+    vfx_conv_desc d = conv_base(in, 1, 1, (int)M, 512, getw(c, q + ".wih", (size_t)1536 * 512, prec), 1536);
     d.ntaps = 1;
     d.bias = getf(c, q + ".bih", 1536);
     set_raw(d, gi, 1536, 0);
     const float* whh = getf(c, q + ".whh_t", (size_t)2 * 256 * 768);
     const float* bhh = getf(c, q + ".bhh", 2 * 768);
+    VFX_TRY(run_conv(c, prec, d, "dn.gru_in"));
     if (!c.dry && c.rc == VFX_OK) {
-      { ProfScope ps(c, "dn.gru_in", conv_flops(d), 0.0); VFX_TRY(conv_gemm_simt(VFX_PREC_FP32, d, c.st)); }
-      { ProfScope ps(c, "dn.gru", 2.0 * M * 2 * 768 * 256, 0.0); VFX_TRY(gru_layer(gi, whh, bhh, B, T, outs[layer], c.st)); }
+      ProfScope ps(c, "dn.gru", 2.0 * M * 2 * 768 * 256, 0.0);
+      VFX_TRY(gru_layer(gi, whh, bhh, B, T, outs[layer], c.st));
     }
-    in = outs[layer];
+    if (layer == 0) { int rc; in = dn_operand(c, y0, M, 512, op, &rc); VFX_TRY(rc); }
   }
   return c.rc;
 }
 
+int relu_inplace(Ctx& c, float* x, int B, int T, int C) {
+  if (c.dry) return VFX_OK;
+  return bn_act(VFX_PREC_FP32, x, (long long)T * C, C, B, T, C, nullptr, nullptr, 1, 0, VFX_ACT_LRELU, 0.f, x,
+                (long long)T * C, C, c.st);
+}
+
 int denoiser_forward(Ctx& c, const float* mel, int B, int T, const uint8_t* drop, float* lin_out) {
   const long long M = (long long)B * T;
-  float* a = c.ws->alloc<float>(M * 512);
+  const int prec = c.prec();
+  void* a = c.ws->alloc<float>(M * 512);          // operand scratch (fp32-sized)
   float* b = c.ws->alloc<float>(M * 512);
   float* y0 = c.ws->alloc<float>(M * 512);
   float* gi = c.ws->alloc<float>(M * 1536);
   const std::string p = "dn.";
-  VFX_TRY(bn_act_op(c, VFX_PREC_FP32, p + "bn0", 1, mel, (long long)T * 128, 128, B, T, 128, VFX_ACT_NONE, 0.f, a));
-  VFX_TRY(linear(c, a, M, 128, p + "lin1", 256, nullptr, b, VFX_ACT_LRELU));         // ReLU (slope 0)
-  VFX_TRY(bn_act_op(c, VFX_PREC_FP32, p + "bn3", 1, b, (long long)T * 256, 256, B, T, 256, VFX_ACT_NONE, 0.f, a));
+  VFX_TRY(bn_act_op(c, prec, p + "bn0", 1, mel, (long long)T * 128, 128, B, T, 128, VFX_ACT_NONE, 0.f, a));
+  VFX_TRY(linear(c, a, M, 128, p + "lin1", 256, b, nullptr, 0));
+  VFX_TRY(relu_inplace(c, b, B, T, 256));
+  VFX_TRY(bn_act_op(c, prec, p + "bn3", 1, b, (long long)T * 256, 256, B, T, 256, VFX_ACT_NONE, 0.f, a));
   VFX_TRY(linear(c, a, M, 256, p + "lin4", 512, b, nullptr, 0));
   if (c.train() && drop && !c.dry) VFX_TRY(dropout_apply(b, drop, M * 512, c.st));
-  if (!c.dry) VFX_TRY(bn_act(VFX_PREC_FP32, b, (long long)T * 512, 512, B, T, 512, nullptr, nullptr, 1, 0, VFX_ACT_LRELU,
-                             0.f, b, (long long)T * 512, 512, c.st));                   // ReLU in place
+  VFX_TRY(relu_inplace(c, b, B, T, 512));
   VFX_TRY(bn_gru(c, p + "g7", b, B, T, a, gi, y0, b));       // result in b
   VFX_TRY(bn_gru(c, p + "g8", b, B, T, a, gi, y0, b));
-  VFX_TRY(bn_act_op(c, VFX_PREC_FP32, p + "bn9", 1, b, (long long)T * 512, 512, B, T, 512, VFX_ACT_LRELU, 0.f, a));
+  VFX_TRY(bn_act_op(c, prec, p + "bn9", 1, b, (long long)T * 512, 512, B, T, 512, VFX_ACT_LRELU, 0.f, a));
   VFX_TRY(linear(c, a, M, 512, p + "lin11", 512, b, nullptr, 0));
   if (c.train() && drop && !c.dry) VFX_TRY(dropout_apply(b, drop + M * 512, M * 512, c.st));
-  VFX_TRY(bn_act_op(c, VFX_PREC_FP32, p + "bn13", 1, b, (long long)T * 512, 512, B, T, 512, VFX_ACT_LRELU, 0.f, a));
+  VFX_TRY(bn_act_op(c, prec, p + "bn13", 1, b, (long long)T * 512, 512, B, T, 512, VFX_ACT_LRELU, 0.f, a));
   VFX_TRY(linear(c, a, M, 512, p + "lin15", 128, lin_out, nullptr, 0));
   return c.rc;
 }
@@ -488,7 +505,9 @@ int vocoder_generator(Ctx& c, const void* cond, int B, int Tc, float* wav_out, i
         for (int k = 0; k < 3; ++k) { d.dw[k] = (k - 1) * dil; d.w_off[k] = (long long)k * Co * Co; }
         d.bias = getf(c, p + ".c1.b", Co);
         set_act(d, Hh, Co, 0, VFX_ACT_LRELU, 0.01f);
-        VFX_TRY(run_conv(c, prec, d, c1_tag));
+        char c1d[48];
+        snprintf(c1d, sizeof(c1d), "%s.d%d", c1_tag, dil);
+        VFX_TRY(run_conv(c, prec, d, c.e->profile > 1 ? c1d : c1_tag));
       }
       {
         vfx_conv_desc d = conv_base(Hh, B, 1, (int)Lout, Co, getw(c, p + ".c2.w", (size_t)3 * Co * Co, prec), Co);

@@ -82,18 +82,18 @@ def pack_analysis(sd, precision="fp32"):
         if idx.numel():
             start[m] = int(idx[0]); length[m] = int(idx[-1]) - int(idx[0]) + 1
     out["fe.fbT"], out["fe.fb_start"], out["fe.fb_len"] = fbT, start, length
-    # ---- denoiser (always fp32)
+    # ---- denoiser (GEMM weights in the operand precision; GRU recurrence weights always fp32)
     d = "generator.denoiser."
     for ref, name in (("0", "bn0"), ("3", "bn3"), ("7.bn", "g7.bn"), ("8.bn", "g8.bn"), ("9", "bn9"), ("13", "bn13")):
         _bn(out, "dn." + name, sd, d + ref)
     for ref, name in (("1", "lin1"), ("4", "lin4"), ("11", "lin11"), ("15", "lin15")):
-        out[f"dn.{name}.w"] = sd[d + ref + ".weight"].float().contiguous()
+        out[f"dn.{name}.w"] = sd[d + ref + ".weight"].float().contiguous().to(wdt)
         out[f"dn.{name}.b"] = sd[d + ref + ".bias"].float()
     for g in ("7", "8"):
         for layer in (0, 1):
             p = f"{d}{g}.gru."
             sfx = [f"_l{layer}", f"_l{layer}_reverse"]
-            out[f"dn.g{g}.l{layer}.wih"] = torch.cat([sd[p + "weight_ih" + s].float() for s in sfx], 0).contiguous()
+            out[f"dn.g{g}.l{layer}.wih"] = torch.cat([sd[p + "weight_ih" + s].float() for s in sfx], 0).contiguous().to(wdt)
             out[f"dn.g{g}.l{layer}.bih"] = torch.cat([sd[p + "bias_ih" + s].float() for s in sfx], 0).contiguous()
             out[f"dn.g{g}.l{layer}.whh_t"] = torch.stack([sd[p + "weight_hh" + s].float().t() for s in sfx], 0).contiguous()
             out[f"dn.g{g}.l{layer}.bhh"] = torch.stack([sd[p + "bias_hh" + s].float() for s in sfx], 0).contiguous()
