@@ -57,8 +57,11 @@ struct TcParams {
   uint32_t epi_warp_bytes, epi_at_off;   // TMA epilogue: per-warp staging bytes, offset of the bf16 tiles
   uint32_t nacc;            // TMEM accumulator stages (2..8): depth of the MMA <-> epilogue pipeline
   int d_nt, d_iw, d_ih, d_b; // mixed-radix digits of gridDim.x in (n_nt, n_tw, n_th, B): per-iteration tile increment
-  uint32_t halo;            // 1-D conv, taps (-d,0,+d), d <= 64: ONE (128+2d)-row box per tile, taps = row-shifted views
-  uint32_t halo_d, halo_rows, halo_kc_bytes;
+  uint32_t halo;            // ONE box per tile, taps = row-shifted views of it: 1-D taps (-d,0,+d) with d <= 64
+                            // [(128+2d) rows], or 3x3 [(th+2) x tw rows starting at (w0-1, h0-1)]
+  uint32_t halo_rows, halo_kc_bytes;   // rows of the TMA box, bytes of one K-chunk block (rows rounded up + zero pad rows)
+  int halo_pw, halo_ph;                // the box starts at (w0 - pw, h0 - ph)
+  uint32_t halo_off[9];                // row offset of each tap's 128-row view inside the box
   uint32_t jtiles;          // tiles whose k-steps are interleaved (independent accumulators hide MMA latency)
   long long* dbg;           // optional per-CTA role counters (VFX_TC_DEBUG)
   int bw_log2;              // TMA epilogue: a warp's 32 rows form a (32/bw) x bw sub-patch, bw = min(tw, 32)
@@ -232,6 +235,14 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   }
   if (p.tma_epi)
     for (int i = threadIdx.x; i < p.bias_mod; i += NUM_THREADS) bias_s[i] = p.bias ? p.bias[i] : 0.f;
+  if (p.halo) {   // rows behind the TMA box (read by the last taps' views, never written by TMA) must be zero
+    const uint32_t row_b = (uint32_t)(p.KC * 2), used = p.halo_rows * row_b, blk = p.halo_kc_bytes;
+    const uint32_t nblk = (uint32_t)p.stages * (uint32_t)p.n_kc, padw = (blk - used) / 4;
+    if (padw)
+      for (uint32_t i = threadIdx.x; i < nblk * padw; i += NUM_THREADS)
+        reinterpret_cast<uint32_t*>(smem + (size_t)(i / padw) * blk + used)[i % padw] = 0u;
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -266,10 +277,10 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           mbar_wait_t(&empty[s], ph ^ 1, w_empty, dbg);
           uint8_t* sa = smem + (size_t)s * stage_bytes;
           if (elect_one()) {
-            mbar_expect_tx(&full[s], p.halo_rows * 128u * (uint32_t)p.n_kc);
+            mbar_expect_tx(&full[s], p.halo_rows * (uint32_t)(p.KC * 2) * (uint32_t)p.n_kc);
 #pragma unroll 1
             for (int kc = 0; kc < p.n_kc; ++kc)
-              tma_load_4d(&tmA, &full[s], sa + (size_t)kc * p.halo_kc_bytes, kc * 64, t.w0 - (int)p.halo_d, 0, t.b);
+              tma_load_4d(&tmA, &full[s], sa + (size_t)kc * p.halo_kc_bytes, kc * p.KC, t.w0 - p.halo_pw, t.h0 - p.halo_ph, t.b);
           }
           __syncwarp();
           if (++s == (uint32_t)p.stages) { s = 0; ph ^= 1; }
@@ -328,13 +339,13 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           const uint32_t w_addr = smem_u32(wres);
           if (elect_one()) {
 #pragma unroll 1
-            for (int tap = 0; tap < 3; ++tap) {
+            for (int tap = 0; tap < p.ntaps; ++tap) {
 #pragma unroll 1
               for (int kc = 0; kc < p.n_kc; ++kc) {
-                const uint32_t a_addr = s_addr + (uint32_t)kc * p.halo_kc_bytes + (uint32_t)tap * p.halo_d * 128u;
+                const uint32_t a_addr = s_addr + (uint32_t)kc * p.halo_kc_bytes + p.halo_off[tap] * (uint32_t)(p.KC * 2);
                 const uint32_t b_addr = w_addr + (uint32_t)(tap * p.n_kc + kc) * p.b_stage_bytes;
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
+#pragma unroll 1
+                for (int k = 0; k < kk; ++k) {
                   const uint64_t ad = make_smem_desc(a_addr + k * 32, p.sbo16, p.layout_type);
                   const uint64_t bd = make_smem_desc(b_addr + k * 32, p.sbo16, p.layout_type);
                   tc_mma_bf16(d_tmem, ad, bd, p.idesc, (tap | kc | k) ? 1u : 0u);
@@ -632,7 +643,6 @@ int conv_gemm_tc(const vfx_conv_desc& d, cudaStream_t st) {
   if (!Ntile) return VFX_ERR_UNSUPPORTED;
   if (d.ntaps < 1 || d.ntaps > 9) return VFX_ERR_UNSUPPORTED;
   if (d.a_sW % 8 || d.a_sH % 8 || d.a_sB % 8 || ((uintptr_t)d.a & 15) || ((uintptr_t)d.w & 15)) return VFX_ERR_UNSUPPORTED;
-  if (d.Wq < 2 && d.Hq < 64) return VFX_ERR_UNSUPPORTED;            // degenerate grids (UNet centre): SIMT
   // epilogue vector alignment
   if (d.out_raw && (d.o_sW % 4 || d.o_sH % 4 || d.o_sB % 4 || d.o_col % 4 || ((uintptr_t)d.out_raw & 15))) return VFX_ERR_UNSUPPORTED;
   if (d.out_act && (d.oa_sW % 8 || d.oa_sH % 8 || d.oa_sB % 8 || d.oa_col % 8 || ((uintptr_t)d.out_act & 15))) return VFX_ERR_UNSUPPORTED;
@@ -692,16 +702,36 @@ int conv_gemm_tc(const vfx_conv_desc& d, cudaStream_t st) {
   const uint32_t epi_smem = p.tma_epi ? NUM_EPI_WARPS * p.epi_warp_bytes + BIAS_SMEM_FLOATS * 4 : 0u;
   if (p.w_resident && p.w_bytes + epi_smem + 3 * p.a_stage_bytes > SMEM_BUDGET) { p.w_resident = 0; p.w_bytes = 0; }
   p.bw_log2 = p.tw_log2 < 5 ? p.tw_log2 : 5;
-  // halo mode: 1-D conv with taps (-d, 0, +d), d <= 64, resident weights, 128-byte rows
+  // halo mode (resident weights): 1-D conv with taps (-d, 0, +d), d <= 64; or a 3x3 conv (taps in kh,kw order)
   static const bool allow_halo = getenv("VFX_NO_HALO") == nullptr;
   p.halo = 0;
-  if (allow_halo && KC == 64 && d.H == 1 && d.Hq == 1 && d.ntaps == 3 && p.w_resident && tw == TILE_M && d.dw[1] == 0 &&
-      d.dw[2] > 0 && d.dw[2] <= 64 && d.dw[0] == -d.dw[2] && d.dh[0] == 0 && d.dh[1] == 0 && d.dh[2] == 0) {
-    p.halo_d = (uint32_t)d.dw[2];
-    p.halo_rows = TILE_M + 2 * p.halo_d;
-    p.halo_kc_bytes = ((p.halo_rows + 7) / 8) * 8 * 128;
-    // worth it only if at least 3 tiles can be in flight
-    p.halo = ((uint32_t)SMEM_BUDGET - p.w_bytes - epi_smem) / (p.halo_kc_bytes * (uint32_t)p.n_kc) >= 2 ? 1u : 0u;
+  uint32_t halo_box_w = 0, halo_box_h = 0;
+  if (allow_halo && p.w_resident) {
+    const uint32_t row_b = (uint32_t)KC * 2;
+    bool ok = false;
+    uint32_t box_w = 0, box_h = 0, extra = 0;
+    if (d.H == 1 && d.Hq == 1 && d.ntaps == 3 && tw == TILE_M && KC == 64 && d.dw[1] == 0 && d.dw[2] > 0 && d.dw[2] <= 64 &&
+        d.dw[0] == -d.dw[2] && d.dh[0] == 0 && d.dh[1] == 0 && d.dh[2] == 0) {
+      const int dd = d.dw[2];
+      box_w = TILE_M + 2 * dd; box_h = 1; p.halo_pw = dd; p.halo_ph = 0;
+      for (int t = 0; t < 3; ++t) p.halo_off[t] = (uint32_t)(t * dd);
+      ok = true;
+    } else if (d.ntaps == 9 && d.Hq == d.H && d.Wq == d.W) {
+      ok = true;
+      for (int t = 0; t < 9; ++t) {
+        if (d.dh[t] != t / 3 - 1 || d.dw[t] != t % 3 - 1) ok = false;
+        p.halo_off[t] = (uint32_t)((t / 3) * tw + (t % 3));
+      }
+      box_w = (uint32_t)tw; box_h = (uint32_t)th + 2; p.halo_pw = 1; p.halo_ph = 1; extra = 2;
+    }
+    if (ok) {
+      p.halo_rows = box_w * box_h;
+      p.halo_kc_bytes = ((p.halo_rows + extra + 7) / 8) * 8 * row_b;
+      p.halo_kc_bytes = (p.halo_kc_bytes + 1023) / 1024 * 1024;
+      // worth it only if at least 2 tiles can be in flight
+      p.halo = ((uint32_t)SMEM_BUDGET - p.w_bytes - epi_smem) / (p.halo_kc_bytes * (uint32_t)p.n_kc) >= 2 ? 1u : 0u;
+      halo_box_w = box_w; halo_box_h = box_h;
+    }
   }
   const uint32_t stage_bytes = p.halo ? p.halo_kc_bytes * (uint32_t)p.n_kc : p.a_stage_bytes + (p.w_resident ? 0u : p.b_stage_bytes);
   int stages = (int)((SMEM_BUDGET - p.w_bytes - epi_smem) / stage_bytes);
@@ -719,7 +749,7 @@ int conv_gemm_tc(const vfx_conv_desc& d, cudaStream_t st) {
     cuuint64_t dims[4] = {(cuuint64_t)d.Cin, (cuuint64_t)d.W, (cuuint64_t)d.H, (cuuint64_t)d.B};
     cuuint64_t strides[3] = {(cuuint64_t)d.a_sW * 2, (cuuint64_t)d.a_sH * 2, (cuuint64_t)d.a_sB * 2};
     // a degenerate dimension of extent 1 may carry any stride; keep them valid multiples of 16
-    cuuint32_t box[4] = {(cuuint32_t)KC, (cuuint32_t)(p.halo ? p.halo_rows : (uint32_t)tw), (cuuint32_t)th, 1};
+    cuuint32_t box[4] = {(cuuint32_t)KC, (cuuint32_t)(p.halo ? halo_box_w : (uint32_t)tw), (cuuint32_t)(p.halo ? halo_box_h : (uint32_t)th), 1};
     cuuint32_t estr[4] = {1, 1, 1, 1};
     CUresult r = encode(&tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(d.a), dims, strides, box, estr,
                         CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,

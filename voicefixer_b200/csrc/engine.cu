@@ -203,7 +203,9 @@ int conv_block(Ctx& c, const std::string& p, const float* in, long long ld_in, i
     vfx_conv_desc d = conv_base(s.opA, B, H, W, Cin, getw(c, p + ".conv1.w", (size_t)9 * Cout * Cin, prec), Cout);
     taps3x3(d, (long long)Cout * Cin);
     set_raw(d, s.rawH, Cout, 0);
-    VFX_TRY(run_conv(c, prec, d, "unet.conv3x3"));
+    char tg[64];
+    snprintf(tg, sizeof(tg), "unet.conv3x3.W%d.%dto%d", W, Cin, Cout);
+    VFX_TRY(run_conv(c, prec, d, c.e->profile > 1 ? tg : "unet.conv3x3"));
   }
   VFX_TRY(bn_act_op(c, prec, p + ".bn2", Cout, s.rawH, P * Cout, Cout, B, P, Cout, VFX_ACT_LRELU, 0.01f, s.opH));
   const float* res = in; long long ld_res = ld_in;
@@ -226,7 +228,9 @@ int conv_block(Ctx& c, const std::string& p, const float* in, long long ld_in, i
     taps3x3(d, (long long)Cout * Cout);
     set_res(d, res, ld_res, 0);
     set_raw(d, out, ld_out, 0);
-    VFX_TRY(run_conv(c, prec, d, "unet.conv3x3"));
+    char tg[64];
+    snprintf(tg, sizeof(tg), "unet.conv3x3.W%d.%dto%d.res", W, Cout, Cout);
+    VFX_TRY(run_conv(c, prec, d, c.e->profile > 1 ? tg : "unet.conv3x3"));
   }
   return c.rc;
 }
