@@ -53,6 +53,9 @@ def test_weight_packing_shapes(states):
     pa = weights.pack_analysis(states[0], "fp32")
     pv = weights.pack_vocoder(states[1], "bf16")
     assert tuple(pa["unet.enc1.b1.conv1.w"].shape) == (9, 32, 2)
+    pb = weights.pack_analysis(states[0], "bf16")              # bf16: Cin 2 zero-padded to 32 operand channels
+    assert tuple(pb["unet.enc1.b1.conv1.w"].shape) == (9, 32, 32) and tuple(pb["unet.enc1.b1.sc.w"].shape) == (32, 32)
+    assert float(pb["unet.enc1.b1.conv1.w"][:, :, 2:].abs().max()) == 0.0
     assert tuple(pa["unet.dec1.up.w"].shape) == (9, 384, 384)
     assert tuple(pa["dn.g7.l0.whh_t"].shape) == (2, 256, 768)
     assert tuple(pv["voc.up0.w"].shape) == (14, 512, 1024) and pv["voc.up0.w"].dtype == torch.bfloat16

@@ -198,10 +198,25 @@ int conv_block(Ctx& c, const std::string& p, const float* in, long long ld_in, i
                int Cin, int Cout, float* out, long long ld_out, const BlockScratch& s) {
   const int prec = c.prec();
   const long long P = (long long)H * W;
-  VFX_TRY(bn_act_op(c, prec, p + ".bn1", Cin, in, P * ld_in, ld_in, B, P, Cin, VFX_ACT_LRELU, 0.01f, s.opA));
+  // bf16 mode: a 2-channel input (first encoder block) is zero-padded to 32 operand channels so the block
+  // runs on the tensor-core kernel; the host packs conv1 / shortcut weights as [..][Cout][32] accordingly.
+  const int Cop = (prec == VFX_PREC_BF16 && Cin < 32) ? 32 : Cin;
+  if (Cop != Cin && !c.dry) {
+    VFX_CUDA_CHECK(cudaMemsetAsync(s.opA, 0, (size_t)B * P * Cop * 2, c.st));
+    VFX_CUDA_CHECK(cudaMemsetAsync(s.opX, 0, (size_t)B * P * Cop * 2, c.st));
+  }
   {
-    vfx_conv_desc d = conv_base(s.opA, B, H, W, Cin, getw(c, p + ".conv1.w", (size_t)9 * Cout * Cin, prec), Cout);
-    taps3x3(d, (long long)Cout * Cin);
+    BnRef r;
+    VFX_TRY(bn_resolve(c, p + ".bn1", Cin, in, P * ld_in, ld_in, B, P, Cin, &r));
+    if (!c.dry) {
+      ProfScope ps(c, "bn_act", 0.0, (double)B * P * Cin * 6);
+      VFX_TRY(bn_act(prec, in, P * ld_in, ld_in, B, P, Cin, r.scale, r.shift, Cin, r.stat_sB, VFX_ACT_LRELU, 0.01f, s.opA,
+                     P * Cop, Cop, c.st));
+    }
+  }
+  {
+    vfx_conv_desc d = conv_base(s.opA, B, H, W, Cop, getw(c, p + ".conv1.w", (size_t)9 * Cout * Cop, prec), Cout);
+    taps3x3(d, (long long)Cout * Cop);
     set_raw(d, s.rawH, Cout, 0);
     char tg[64];
     snprintf(tg, sizeof(tg), "unet.conv3x3.W%d.%dto%d", W, Cin, Cout);
@@ -213,10 +228,10 @@ int conv_block(Ctx& c, const std::string& p, const float* in, long long ld_in, i
     const void* xin = in;
     if (prec != VFX_PREC_FP32 || ld_in != Cin) {   // shortcut consumes raw x as a dense operand
       if (!c.dry) VFX_TRY(bn_act(prec, in, P * ld_in, ld_in, B, P, Cin, nullptr, nullptr, Cin, 0, VFX_ACT_NONE, 0.f,
-                                 s.opX, P * Cin, Cin, c.st));
+                                 s.opX, P * Cop, Cop, c.st));
       xin = s.opX;
     }
-    vfx_conv_desc d = conv_base(xin, B, H, W, Cin, getw(c, p + ".sc.w", (size_t)Cout * Cin, prec), Cout);
+    vfx_conv_desc d = conv_base(xin, B, H, W, Cop, getw(c, p + ".sc.w", (size_t)Cout * Cop, prec), Cout);
     d.ntaps = 1;
     d.bias = getf(c, p + ".sc.b", Cout);
     set_raw(d, s.rawS, Cout, 0);

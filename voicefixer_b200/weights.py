@@ -57,11 +57,16 @@ def _conv_block(out, name, sd, p, wdt):
     _bn(out, name + ".bn1", sd, p + ".bn1")
     _bn(out, name + ".bn2", sd, p + ".bn2")
     w1, w2 = sd[p + ".conv1.weight"].float(), sd[p + ".conv2.weight"].float()
+    pad_cin = wdt == torch.bfloat16 and w1.shape[1] < 32      # tensor-core path: zero-pad tiny Cin to 32 operand channels
+    if pad_cin:
+        w1 = torch.nn.functional.pad(w1, (0, 0, 0, 0, 0, 32 - w1.shape[1]))
     out[name + ".conv1.w"] = w1.permute(2, 3, 0, 1).reshape(9, w1.shape[0], w1.shape[1]).contiguous().to(wdt)
     out[name + ".conv2.w"] = w2.permute(2, 3, 0, 1).reshape(9, w2.shape[0], w2.shape[1]).contiguous().to(wdt)
     if p + ".shortcut.weight" in sd:
-        ws = sd[p + ".shortcut.weight"].float()
-        out[name + ".sc.w"] = ws[:, :, 0, 0].contiguous().to(wdt)
+        ws = sd[p + ".shortcut.weight"].float()[:, :, 0, 0]
+        if pad_cin:
+            ws = torch.nn.functional.pad(ws, (0, 32 - ws.shape[1]))
+        out[name + ".sc.w"] = ws.contiguous().to(wdt)
         out[name + ".sc.b"] = sd[p + ".shortcut.bias"].float()
 
 
