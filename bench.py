@@ -277,22 +277,30 @@ def main():
     rep = eng.profile_report()
     eng.profile(False)
     tot_ms = sum(r["ms"] for r in rep.values())
-    dom_tag = max((t for t in rep if rep[t]["flops"] > 0), key=lambda t: rep[t]["ms"])
+    # dominant launch group = most time among the single-shape conv tags (8 identical launches per tag)
+    cand = [t for t in rep if rep[t]["flops"] > 0 and rep[t]["bytes"] > 0 and t.startswith("voc.rs")]
+    dom_tag = max(cand or [t for t in rep if rep[t]["flops"] > 0], key=lambda t: rep[t]["ms"])
     dom = rep[dom_tag]
-    per_launch_flops = dom["flops"] / dom["count"]
     per_launch_ms = dom["ms"] / dom["count"]
-    achieved = per_launch_flops / (per_launch_ms * 1e-3) / 1e12
-    peak = peaks["bf16_tflops_sustained"]
+    flops_l, bytes_l = dom["flops"] / dom["count"], dom["bytes"] / dom["count"]
+    tf = flops_l / (per_launch_ms * 1e-3) / 1e12
+    gbs = bytes_l / (per_launch_ms * 1e-3) / 1e9
+    ridge = peaks["bf16_tflops_sustained"] * 1e3 / peaks["hbm_gbs"]                  # FLOP per byte
+    hbm_bound = (flops_l / max(bytes_l, 1.0)) < ridge
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
     if os.path.exists(tpath):
-        traffic = json.load(open(tpath)).get(f"{args.precision}:{dom_tag}")
-    roofline = {"bound": "tensor", "kernel": dom_tag, "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                "frac": achieved / peak, "traffic": traffic, "peak_source": f"{peaks_src} bf16_tflops_sustained",
-                "launches_in_step": dom["count"], "avg_launch_ms": per_launch_ms,
-                "share_of_step": dom["ms"] / tot_ms,
-                "whole_step": {"tflops": FLOP_PER_AUDIO_SEC * B * args.seconds / (ms_step * 1e-3) / 1e12 / 1.0,
-                               "frac": FLOP_PER_AUDIO_SEC * B * args.seconds / (ms_step * 1e-3) / 1e12 / peak}}
+        traffic = json.load(open(tpath)).get(f"{args.precision}:{dom_tag}:B{B}")
+    whole_tf = FLOP_PER_AUDIO_SEC * B * args.seconds / (ms_step * 1e-3) / 1e12
+    roofline = {"bound": "hbm" if hbm_bound else "tensor", "kernel": f"conv_gemm_tc_kernel [{dom_tag}]",
+                "achieved": gbs if hbm_bound else tf, "peak": peaks["hbm_gbs"] if hbm_bound else peaks["bf16_tflops_sustained"],
+                "unit": "GB/s" if hbm_bound else "TFLOP/s",
+                "frac": (gbs / peaks["hbm_gbs"]) if hbm_bound else (tf / peaks["bf16_tflops_sustained"]),
+                "traffic": traffic, "peak_source": f"{peaks_src} ({'hbm_gbs' if hbm_bound else 'bf16_tflops_sustained'})",
+                "algorithmic_bytes_per_launch": bytes_l, "algorithmic_flops_per_launch": flops_l,
+                "launches_in_step": dom["count"], "avg_launch_ms": per_launch_ms, "share_of_step": dom["ms"] / tot_ms,
+                "other": {"tflops": tf, "gbs": gbs, "flop_per_byte": flops_l / max(bytes_l, 1.0), "ridge": ridge},
+                "whole_step": {"tflops": whole_tf, "frac_of_bf16_sustained": whole_tf / peaks["bf16_tflops_sustained"]}}
     breakdown = {t: round(r["ms"], 3) for t, r in sorted(rep.items(), key=lambda kv: -kv[1]["ms"])}
 
     cpu_baseline = None

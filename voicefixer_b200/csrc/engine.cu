@@ -93,6 +93,13 @@ struct ProfScope {
 double conv_flops(const vfx_conv_desc& d) {
   return 2.0 * d.B * d.Hq * d.Wq * (double)d.N * d.Cin * d.ntaps;
 }
+// algorithmic HBM bytes of one conv launch: the input tensor once (taps re-read from L2), fp32 residual in,
+// fp32 raw out, operand out (weights are negligible and stay in L2)
+double conv_bytes(const vfx_conv_desc& d, int prec) {
+  const double esz = prec == VFX_PREC_BF16 ? 2.0 : 4.0;
+  const double M = (double)d.B * d.Hq * d.Wq;
+  return (double)d.B * d.H * d.W * d.Cin * esz + M * d.N * ((d.residual ? 4.0 : 0.0) + (d.out_raw ? 4.0 : 0.0) + (d.out_act ? esz : 0.0));
+}
 
 #define VFX_TRY(expr) do { int _r = (expr); if (_r != VFX_OK) return _r; } while (0)
 
@@ -119,7 +126,7 @@ const void* getw(Ctx& c, const std::string& name, size_t n, int prec) {
 int run_conv(Ctx& c, int prec, const vfx_conv_desc& d, const char* tag = "conv") {
   if (c.dry) return VFX_OK;
   if (c.rc != VFX_OK) return c.rc;
-  ProfScope ps(c, tag, conv_flops(d), 0.0);
+  ProfScope ps(c, tag, conv_flops(d), conv_bytes(d, prec));
   if (prec == VFX_PREC_BF16 && c.e->use_tc) {
     int r = conv_gemm_tc(d, c.st);
     if (r != VFX_ERR_UNSUPPORTED) return r;
