@@ -134,6 +134,8 @@ typedef struct vfx_conv_desc {
   long long r_sB, r_sH, r_sW; int r_col;
   int act;                  /* vfx_act applied to out_act */
   float act_param;          /* leaky slope */
+  const float* act_scale;   /* optional per-channel affine before the activation of out_act:          */
+  const float* act_shift;   /* out_act = act(result * act_scale[n] + act_shift[n]) (fused eval-mode BN) */
 } vfx_conv_desc;
 
 enum vfx_act { VFX_ACT_NONE = 0, VFX_ACT_LRELU = 1, VFX_ACT_ELU = 2,

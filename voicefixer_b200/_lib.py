@@ -28,7 +28,7 @@ class ConvDesc(ctypes.Structure):
         ("out_act", _vp), ("oa_sB", _ll), ("oa_sH", _ll), ("oa_sW", _ll), ("oa_col", _i),
         ("bias", _vp), ("bias_mod", _i),
         ("residual", _vp), ("r_sB", _ll), ("r_sH", _ll), ("r_sW", _ll), ("r_col", _i),
-        ("act", _i), ("act_param", _f),
+        ("act", _i), ("act_param", _f), ("act_scale", _vp), ("act_shift", _vp),
     ]
 
 

@@ -140,9 +140,11 @@ __global__ void __launch_bounds__(NT) conv_gemm_simt_kernel(const vfx_conv_desc 
         v += d.residual[(long long)b * d.r_sB + (long long)oh * d.r_sH + (long long)ow * d.r_sW + d.r_col + n];
       if (d.out_raw)
         d.out_raw[(long long)b * d.o_sB + (long long)oh * d.o_sH + (long long)ow * d.o_sW + d.o_col + n] = v;
-      if (out_act)
+      if (out_act) {
+        const float va = d.act_scale ? fmaf(v, d.act_scale[n], d.act_shift[n]) : v;
         out_act[(long long)b * d.oa_sB + (long long)oh * d.oa_sH + (long long)ow * d.oa_sW + d.oa_col + n] =
-            from_f<T>(apply_act(v, d.act, d.act_param));
+            from_f<T>(apply_act(va, d.act, d.act_param));
+      }
     }
   }
 }

@@ -45,6 +45,7 @@ struct TcParams {
   const float* bias; int bias_mod;
   const float* residual; long long r_sB, r_sH, r_sW; int r_col;
   int act; float act_param;
+  const float* act_scale; const float* act_shift;   // optional affine before the activation of out_act
   uint32_t idesc;           // tcgen05 instruction descriptor
   uint32_t a_stage_bytes, b_stage_bytes;
   uint32_t sbo16;           // stride-byte-offset >> 4 of the K-major swizzled layout (8 rows)
@@ -209,7 +210,9 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   const uint32_t stage_bytes = p.halo ? p.halo_kc_bytes * (uint32_t)p.n_kc : p.a_stage_bytes + (p.w_resident ? 0u : p.b_stage_bytes);
   uint8_t* staging = smem + (size_t)p.stages * stage_bytes;
   float* bias_s = reinterpret_cast<float*>(staging + (p.tma_epi ? NUM_EPI_WARPS * p.epi_warp_bytes : 0));
-  uint64_t* bars = reinterpret_cast<uint64_t*>(bias_s + (p.tma_epi ? BIAS_SMEM_FLOATS : 0));
+  float* asc_s = bias_s + BIAS_SMEM_FLOATS;             // act_scale / act_shift copies (TMA epilogue)
+  float* ash_s = asc_s + BIAS_SMEM_FLOATS;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(bias_s + (p.tma_epi ? 3 * BIAS_SMEM_FLOATS : 0));
   uint64_t* full = bars;
   uint64_t* empty = bars + p.stages;
   uint64_t* tmem_full = bars + 2 * p.stages;
@@ -234,7 +237,11 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   if (p.tma_epi)
-    for (int i = threadIdx.x; i < p.bias_mod; i += NUM_THREADS) bias_s[i] = p.bias ? p.bias[i] : 0.f;
+    for (int i = threadIdx.x; i < p.N; i += NUM_THREADS) {
+      bias_s[i] = p.bias ? p.bias[i % p.bias_mod] : 0.f;
+      asc_s[i] = p.act_scale ? p.act_scale[i] : 1.f;
+      ash_s[i] = p.act_scale ? p.act_shift[i] : 0.f;
+    }
   if (p.halo) {   // rows behind the TMA box (read by the last taps' views, never written by TMA) must be zero
     const uint32_t row_b = (uint32_t)(p.KC * 2), used = p.halo_rows * row_b, blk = p.halo_kc_bytes;
     const uint32_t nblk = (uint32_t)p.stages * (uint32_t)p.n_kc, padw = (blk - used) / 4;
@@ -424,7 +431,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       const long long td0 = dbg ? clock64() : 0;
       const TileCoord t = eit.coord(p);
       eit.next(p);                                      // eit now points at this CTA's next tile
-      uint32_t bcol = (uint32_t)t.n0 + half * 32;       // plain convs: bias_mod >= N, no modulo
+      uint32_t bcol = (uint32_t)t.n0 + half * 32;       // bias_s is pre-tiled over the N columns
       if (dbg) w_dec += clock64() - td0;
       mbar_wait_t(&tmem_full[acc], acc_ph, w_tf, dbg);
       tc_fence_after();
@@ -462,6 +469,16 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         }
         if (p.out_act) {
           uint8_t* const at = at_base + k * 2048 + lane * 64;
+          if (p.act_scale) {                          // fused eval-mode BatchNorm of the consumer
+            const float4* sp = reinterpret_cast<const float4*>(asc_s + bcol - 64);
+            const float4* tp = reinterpret_cast<const float4*>(ash_s + bcol - 64);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float4 s4 = sp[j], t4 = tp[j];
+              f[4 * j] = fmaf(f[4 * j], s4.x, t4.x); f[4 * j + 1] = fmaf(f[4 * j + 1], s4.y, t4.y);
+              f[4 * j + 2] = fmaf(f[4 * j + 2], s4.z, t4.z); f[4 * j + 3] = fmaf(f[4 * j + 3], s4.w, t4.w);
+            }
+          }
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             uint32_t w[4];
@@ -578,6 +595,16 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             for (int j = 0; j < 8; ++j) op[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
           }
           if (p.out_act) {
+            if (p.act_scale) {
+              const float4* sp = reinterpret_cast<const float4*>(p.act_scale + n);
+              const float4* tp = reinterpret_cast<const float4*>(p.act_shift + n);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const float4 s4 = __ldg(sp + j), t4 = __ldg(tp + j);
+                f[4 * j] = fmaf(f[4 * j], s4.x, t4.x); f[4 * j + 1] = fmaf(f[4 * j + 1], s4.y, t4.y);
+                f[4 * j + 2] = fmaf(f[4 * j + 2], s4.z, t4.z); f[4 * j + 3] = fmaf(f[4 * j + 3], s4.w, t4.w);
+              }
+            }
             uint4* ap = reinterpret_cast<uint4*>(p.out_act + off_a + c0);
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
@@ -675,6 +702,7 @@ int conv_gemm_tc(const vfx_conv_desc& d, cudaStream_t st) {
   p.bias = d.bias; p.bias_mod = d.bias_mod > 0 ? d.bias_mod : d.N;
   p.residual = d.residual; p.r_sB = d.r_sB; p.r_sH = d.r_sH; p.r_sW = d.r_sW; p.r_col = d.r_col;
   p.act = d.act; p.act_param = d.act_param;
+  p.act_scale = d.out_act ? d.act_scale : nullptr; p.act_shift = d.out_act ? d.act_shift : nullptr;
   // instruction descriptor: c=F32 [4,6)=1, a=BF16 [7,10)=1, b=BF16 [10,13)=1, K-major both, N>>3 [17,23), M>>4 [24,29)
   p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(Ntile >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
   const uint32_t row_bytes = KC * 2;
@@ -694,12 +722,12 @@ int conv_gemm_tc(const vfx_conv_desc& d, cudaStream_t st) {
   // plain stride-1 convolution whose output grid is the tensor itself -> TMA-staged epilogue
   static const bool allow_tma_epi = getenv("VFX_NO_TMA_EPI") == nullptr;
   p.tma_epi = (allow_tma_epi && d.sh == 1 && d.sw == 1 && d.rh == 0 && d.rw == 0 && d.OH == d.Hq && d.OW == d.Wq) ? 1u : 0u;
-  if (p.tma_epi && (p.bias_mod > BIAS_SMEM_FLOATS || p.bias_mod < d.N)) p.tma_epi = 0;
+  if (p.tma_epi && d.N > BIAS_SMEM_FLOATS) p.tma_epi = 0;
   p.epi_arrivals = 32u * NUM_EPI_WARPS;
   const bool needs_ro = d.out_raw || d.residual;
   p.epi_at_off = needs_ro ? 8192u : 0u;
   p.epi_warp_bytes = p.epi_at_off + (d.out_act ? 4096u : 0u);
-  const uint32_t epi_smem = p.tma_epi ? NUM_EPI_WARPS * p.epi_warp_bytes + BIAS_SMEM_FLOATS * 4 : 0u;
+  const uint32_t epi_smem = p.tma_epi ? NUM_EPI_WARPS * p.epi_warp_bytes + 3 * BIAS_SMEM_FLOATS * 4 : 0u;
   if (p.w_resident && p.w_bytes + epi_smem + 3 * p.a_stage_bytes > SMEM_BUDGET) { p.w_resident = 0; p.w_bytes = 0; }
   p.bw_log2 = p.tw_log2 < 5 ? p.tw_log2 : 5;
   // halo mode (resident weights): 1-D conv with taps (-d, 0, +d), d <= 64; or a 3x3 conv (taps in kh,kw order)

@@ -201,10 +201,18 @@ int bn_act_op(Ctx& c, int prec, const std::string& bn, int bn_C, const float* x,
 // in: raw fp32 [B][H][W][Cin] with pitch ld_in; out: raw fp32 with pitch ld_out (+col), may alias in.
 struct BlockScratch { void* opA; float* rawH; void* opH; float* rawS; void* opX; };
 
+// Eval-mode fusion hooks of a block (ignored in mode 2, which needs batch statistics between the ops):
+//   opA_ready : s.opA already holds lrelu(bn1(in)) -- written by the previous conv's epilogue
+//   next_bn   : BatchNorm whose eval affine + activation conv2's epilogue applies to produce the NEXT
+//               consumer's operand in s.opA (next_slope: 0.01 LeakyReLU for ConvBlockRes.bn1, 0 = ReLU for
+//               DecoderBlockRes.bn1)
+struct BlockFuse { bool opA_ready = false; const char* next_bn = nullptr; float next_slope = 0.01f; };
+
 int conv_block(Ctx& c, const std::string& p, const float* in, long long ld_in, int B, int H, int W,
-               int Cin, int Cout, float* out, long long ld_out, const BlockScratch& s) {
+               int Cin, int Cout, float* out, long long ld_out, const BlockScratch& s, const BlockFuse& fz = BlockFuse()) {
   const int prec = c.prec();
   const long long P = (long long)H * W;
+  const bool fuse = !c.train();
   // bf16 mode: a 2-channel input (first encoder block) is zero-padded to 32 operand channels so the block
   // runs on the tensor-core kernel; the host packs conv1 / shortcut weights as [..][Cout][32] accordingly.
   const int Cop = (prec == VFX_PREC_BF16 && Cin < 32) ? 32 : Cin;
@@ -212,7 +220,7 @@ int conv_block(Ctx& c, const std::string& p, const float* in, long long ld_in, i
     VFX_CUDA_CHECK(cudaMemsetAsync(s.opA, 0, (size_t)B * P * Cop * 2, c.st));
     VFX_CUDA_CHECK(cudaMemsetAsync(s.opX, 0, (size_t)B * P * Cop * 2, c.st));
   }
-  {
+  if (!(fuse && fz.opA_ready)) {
     BnRef r;
     VFX_TRY(bn_resolve(c, p + ".bn1", Cin, in, P * ld_in, ld_in, B, P, Cin, &r));
     if (!c.dry) {
@@ -221,15 +229,22 @@ int conv_block(Ctx& c, const std::string& p, const float* in, long long ld_in, i
                      P * Cop, Cop, c.st));
     }
   }
-  {
+  char tg[64];
+  if (fuse) {     // conv1 with bn2 folded in: h = lrelu(conv1f(a) + b) straight into the operand buffer
+    vfx_conv_desc d = conv_base(s.opA, B, H, W, Cop, getw(c, p + ".conv1f.w", (size_t)9 * Cout * Cop, prec), Cout);
+    taps3x3(d, (long long)Cout * Cop);
+    d.bias = getf(c, p + ".conv1f.b", Cout);
+    set_act(d, s.opH, Cout, 0, VFX_ACT_LRELU, 0.01f);
+    snprintf(tg, sizeof(tg), "unet.conv3x3.W%d.%dto%d", W, Cin, Cout);
+    VFX_TRY(run_conv(c, prec, d, c.e->profile > 1 ? tg : "unet.conv3x3"));
+  } else {
     vfx_conv_desc d = conv_base(s.opA, B, H, W, Cop, getw(c, p + ".conv1.w", (size_t)9 * Cout * Cop, prec), Cout);
     taps3x3(d, (long long)Cout * Cop);
     set_raw(d, s.rawH, Cout, 0);
-    char tg[64];
     snprintf(tg, sizeof(tg), "unet.conv3x3.W%d.%dto%d", W, Cin, Cout);
     VFX_TRY(run_conv(c, prec, d, c.e->profile > 1 ? tg : "unet.conv3x3"));
+    VFX_TRY(bn_act_op(c, prec, p + ".bn2", Cout, s.rawH, P * Cout, Cout, B, P, Cout, VFX_ACT_LRELU, 0.01f, s.opH));
   }
-  VFX_TRY(bn_act_op(c, prec, p + ".bn2", Cout, s.rawH, P * Cout, Cout, B, P, Cout, VFX_ACT_LRELU, 0.01f, s.opH));
   const float* res = in; long long ld_res = ld_in;
   if (Cin != Cout) {
     const void* xin = in;
@@ -250,7 +265,12 @@ int conv_block(Ctx& c, const std::string& p, const float* in, long long ld_in, i
     taps3x3(d, (long long)Cout * Cout);
     set_res(d, res, ld_res, 0);
     set_raw(d, out, ld_out, 0);
-    char tg[64];
+    if (fuse && fz.next_bn) {   // the consumer's eval BatchNorm + activation, fused: s.opA = act(bn(out))
+      const std::string nb(fz.next_bn);
+      d.act_scale = getf(c, nb + ".scale", Cout);
+      d.act_shift = getf(c, nb + ".shift", Cout);
+      set_act(d, s.opA, Cout, 0, VFX_ACT_LRELU, fz.next_slope);
+    }
     snprintf(tg, sizeof(tg), "unet.conv3x3.W%d.%dto%d.res", W, Cout, Cout);
     VFX_TRY(run_conv(c, prec, d, c.e->profile > 1 ? tg : "unet.conv3x3"));
   }
@@ -284,19 +304,27 @@ int unet_forward(Ctx& c, const float* unet_in, int B, int Tp, float** feat_out) 
   for (int l = 1; l <= 6; ++l) {
     const int H = Hl[l - 1], W = Wl[l - 1], C = UNET_C[l];
     float* skip = cat[l] + C;                     // pitch 2C
+    char nbn[4][96];
     for (int j = 1; j <= 4; ++j) {
       snprintf(name, sizeof(name), "unet.enc%d.b%d", l, j);
-      if (j == 1) VFX_TRY(conv_block(c, name, x, Cx, B, H, W, Cx, C, skip, 2 * C, s));
-      else VFX_TRY(conv_block(c, name, skip, 2 * C, B, H, W, C, C, skip, 2 * C, s));
+      BlockFuse fz;
+      fz.opA_ready = j > 1;                               // produced by block j-1's conv2 epilogue
+      if (j < 4) { snprintf(nbn[j], sizeof(nbn[j]), "unet.enc%d.b%d.bn1", l, j + 1); fz.next_bn = nbn[j]; }
+      if (j == 1) VFX_TRY(conv_block(c, name, x, Cx, B, H, W, Cx, C, skip, 2 * C, s, fz));
+      else VFX_TRY(conv_block(c, name, skip, 2 * C, B, H, W, C, C, skip, 2 * C, s, fz));
     }
     ProfScope ps(c, "unet.pool", 0.0, (double)B * H * W * C * 5.0);
     if (!c.dry) VFX_TRY(avgpool2x2(skip, (long long)H * W * 2 * C, (long long)W * 2 * C, 2 * C, B, H, W, C, pool[l], c.st));
     x = pool[l]; Cx = C;
   }
   // ---- centre block (in place on pool[6]): conv_block7
-  VFX_TRY(conv_block(c, "unet.center", pool[6], 384, B, Hl[6], Wl[6], 384, 384, pool[6], 384, s));
+  {
+    BlockFuse fz; fz.next_bn = "unet.dec1.bn1"; fz.next_slope = 0.0f;      // relu(bn1(x)) before the first ConvTranspose
+    VFX_TRY(conv_block(c, "unet.center", pool[6], 384, B, Hl[6], Wl[6], 384, 384, pool[6], 384, s, fz));
+  }
   float* xd = pool[6];
   int Cd = 384;
+  const bool fuse = !c.train();
   // ---- decoder i = 1..6 at level l = 7 - i  (DecoderBlockRes.forward restorer/modules.py:149-157)
   for (int i = 1; i <= 6; ++i) {
     const int l = 7 - i;
@@ -306,7 +334,8 @@ int unet_forward(Ctx& c, const float* unet_in, int B, int Tp, float** feat_out) 
     snprintf(name, sizeof(name), "unet.dec%d", i);
     const std::string p(name);
     const long long Pin = (long long)H * W;
-    VFX_TRY(bn_act_op(c, prec, p + ".bn1", Cd, xd, Pin * Cd, Cd, B, Pin, Cd, VFX_ACT_LRELU, 0.0f, s.opA));
+    if (!fuse)   // eval: relu(bn1(x)) was written into s.opA by the producing conv2's epilogue
+      VFX_TRY(bn_act_op(c, prec, p + ".bn1", Cd, xd, Pin * Cd, Cd, B, Pin, Cd, VFX_ACT_LRELU, 0.0f, s.opA));
     const void* wt = getw(c, p + ".up.w", (size_t)9 * Cout * Cd, prec);
     for (int rh = 0; rh < 2; ++rh)
       for (int rw = 0; rw < 2; ++rw) {
@@ -326,14 +355,23 @@ int unet_forward(Ctx& c, const float* unet_in, int B, int Tp, float** feat_out) 
     // conv_block2..5: first consumes the concat tensor (2C -> C, with shortcut)
     float* dl = pool[l];                          // dense [B][OH][OW][Cout]: reuse? sizes differ -> own buffer
     dl = c.ws->alloc<float>((size_t)B * OH * OW * Cout);
+    char nbn[96];
     for (int j = 2; j <= 5; ++j) {
       snprintf(name, sizeof(name), "unet.dec%d.b%d", i, j);
-      if (j == 2) VFX_TRY(conv_block(c, name, cat[l], 2 * Cout, B, OH, OW, 2 * Cout, Cout, dl, Cout, s));
-      else VFX_TRY(conv_block(c, name, dl, Cout, B, OH, OW, Cout, Cout, dl, Cout, s));
+      BlockFuse fz;
+      fz.opA_ready = j > 2;
+      if (j < 5) { snprintf(nbn, sizeof(nbn), "unet.dec%d.b%d.bn1", i, j + 1); fz.next_bn = nbn; }
+      else if (i < 6) { snprintf(nbn, sizeof(nbn), "unet.dec%d.bn1", i + 1); fz.next_bn = nbn; fz.next_slope = 0.0f; }
+      else { snprintf(nbn, sizeof(nbn), "unet.after.bn1"); fz.next_bn = nbn; }
+      if (j == 2) VFX_TRY(conv_block(c, name, cat[l], 2 * Cout, B, OH, OW, 2 * Cout, Cout, dl, Cout, s, fz));
+      else VFX_TRY(conv_block(c, name, dl, Cout, B, OH, OW, Cout, Cout, dl, Cout, s, fz));
     }
     xd = dl; Cd = Cout;
   }
-  VFX_TRY(conv_block(c, "unet.after", xd, 32, B, Tp, 127, 32, 32, xd, 32, s));
+  {
+    BlockFuse fz; fz.opA_ready = true;                   // dec6.b5 produced lrelu(after.bn1(x))
+    VFX_TRY(conv_block(c, "unet.after", xd, 32, B, Tp, 127, 32, 32, xd, 32, s, fz));
+  }
   *feat_out = xd;
   return c.rc;
 }
@@ -509,14 +547,17 @@ int vocoder_generator(Ctx& c, const void* cond, int B, int Tc, float* wav_out, i
       const long long mat = (long long)Co * Ci;
       for (int grp = 0; grp < 2; ++grp) {
         const int nph = grp == 0 ? nA : u - nA;
+        // Output described as the reshaped view [B][Lin][u*Co] (row q holds output samples q*u .. q*u+u-1):
+        // the phase group is then a plain stride-1 GEMM writing columns [r0*Co, (r0+nph)*Co) of row q, which
+        // lets the tensor-core kernel use its TMA-staged epilogue.
         vfx_conv_desc d = conv_base(U, B, 1, (int)Lin, Ci, w, nph * Co);
         d.ntaps = 2;
-        if (grp == 0) { d.dw[0] = 0; d.w_off[0] = pad * mat; d.dw[1] = -1; d.w_off[1] = (pad + u) * mat; d.rw = 0; }
-        else          { d.dw[0] = 1; d.w_off[0] = 0;         d.dw[1] = 0;  d.w_off[1] = u * mat;         d.rw = nA; }
-        d.sw = u; d.OW = (int)Lout;
+        int r0;
+        if (grp == 0) { d.dw[0] = 0; d.w_off[0] = pad * mat; d.dw[1] = -1; d.w_off[1] = (pad + u) * mat; r0 = 0; }
+        else          { d.dw[0] = 1; d.w_off[0] = 0;         d.dw[1] = 0;  d.w_off[1] = u * mat;         r0 = nA; }
         d.bias = bias; d.bias_mod = Co;
-        set_raw(d, X, Co, 0);
-        set_act(d, A0, Co, 0, VFX_ACT_LRELU, 0.01f);
+        set_raw(d, X, (long long)u * Co, r0 * Co);
+        set_act(d, A0, (long long)u * Co, r0 * Co, VFX_ACT_LRELU, 0.01f);
         VFX_TRY(run_conv(c, prec, d, up_tag));
       }
     }

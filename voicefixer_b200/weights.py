@@ -62,6 +62,11 @@ def _conv_block(out, name, sd, p, wdt):
         w1 = torch.nn.functional.pad(w1, (0, 0, 0, 0, 0, 32 - w1.shape[1]))
     out[name + ".conv1.w"] = w1.permute(2, 3, 0, 1).reshape(9, w1.shape[0], w1.shape[1]).contiguous().to(wdt)
     out[name + ".conv2.w"] = w2.permute(2, 3, 0, 1).reshape(9, w2.shape[0], w2.shape[1]).contiguous().to(wdt)
+    # eval mode: bn2 folds into conv1 (scale rows, shift as bias) -> conv1f; its epilogue applies the LeakyReLU
+    sc2, sh2 = out[name + ".bn2.scale"], out[name + ".bn2.shift"]
+    w1f = w1 * sc2[:, None, None, None]
+    out[name + ".conv1f.w"] = w1f.permute(2, 3, 0, 1).reshape(9, w1f.shape[0], w1f.shape[1]).contiguous().to(wdt)
+    out[name + ".conv1f.b"] = sh2.clone()
     if p + ".shortcut.weight" in sd:
         ws = sd[p + ".shortcut.weight"].float()[:, :, 0, 0]
         if pad_cin:
