@@ -189,6 +189,24 @@ class Engine:
                                         _stream()), "vfx_restore")
         return out
 
+    def make_graph(self, wav, out, mode=0):
+        """Captures the whole restore() launch sequence (~360 kernels) for the given device buffers into a
+        CUDA graph; returns an object whose .replay() re-runs it (inputs are read from `wav`, results land in
+        `out`).  Shapes, buffers and the workspace are frozen into the graph."""
+        assert wav.is_cuda and out.is_cuda and wav.shape == out.shape
+        self._workspace(self.workspace_bytes(*wav.shape))           # allocate before capture
+        side = torch.cuda.Stream(device=wav.device)
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):                                # warm-up: one-time attribute / table setup
+            for _ in range(2):
+                self.restore(wav, mode=mode, out=out)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            self.restore(wav, mode=mode, out=out)
+        return g
+
     def hf_cut(self, wav, ratio=0.95):
         wav = self._dev(wav)
         B, L = wav.shape
