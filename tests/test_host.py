@@ -139,3 +139,26 @@ def test_oracle_conditions_match_oracle_module():
     b = O.oracle_cond(wav).numpy()                              # (1, 128, Tc)
     assert a.shape == (1, b.shape[2], 128)
     assert np.max(np.abs(a - b.transpose(0, 2, 1))) < 1e-4
+
+
+def test_cli_job_planning_matches_reference_naming(tmp_path):
+    """voicefixer/__main__.py:13-19,147-213: `--mode all` -> <name>-mode<k><ext>; only .wav inputs; folder mode."""
+    from voicefixer_b200.__main__ import build_parser, plan_jobs
+    (tmp_path / "in").mkdir()
+    for n in ("a.wav", "b.wav", "c.txt"):
+        (tmp_path / "in" / n).write_bytes(b"")
+    args = build_parser().parse_args(["-i", str(tmp_path / "in" / "a.wav"), "-o", str(tmp_path / "o" / "r.wav"), "--mode", "all"])
+    jobs = plan_jobs(args)
+    assert [os.path.basename(j[1]) for j in jobs] == ["r-mode0.wav", "r-mode1.wav", "r-mode2.wav"] and [j[2] for j in jobs] == [0, 1, 2]
+    args = build_parser().parse_args(["--infolder", str(tmp_path / "in"), "--outfolder", str(tmp_path / "out"), "--mode", "1"])
+    jobs = plan_jobs(args)
+    assert [os.path.basename(j[0]) for j in jobs] == ["a.wav", "b.wav"] and all(j[2] == 1 for j in jobs)
+    assert os.path.basename(jobs[0][1]) == "a.wav"
+    with pytest.raises(AssertionError, match="--infile"):
+        plan_jobs(build_parser().parse_args([]))
+    with pytest.raises(AssertionError, match="not found"):
+        plan_jobs(build_parser().parse_args(["-i", str(tmp_path / "nope.wav")]))
+    with pytest.raises(AssertionError, match="Unsupported output format"):
+        plan_jobs(build_parser().parse_args(["-i", str(tmp_path / "in" / "a.wav"), "-o", "x.flac"]))
+    with pytest.raises(ValueError, match="only support the .wav"):
+        plan_jobs(build_parser().parse_args(["-i", str(tmp_path / "in" / "c.txt"), "-o", "x.wav"]))

@@ -56,6 +56,7 @@ struct TcParams {
   uint32_t tma_epi;         // plain (stride-1) conv: residual in / raw+operand out through TMA-staged tiles
   uint32_t epi_arrivals;    // threads arriving on tmem_empty
   uint32_t epi_warp_bytes, epi_at_off;   // TMA epilogue: per-warp staging bytes, offset of the bf16 tiles
+  uint32_t bias_floats;     // TMA epilogue: floats per smem array (bias, act_scale, act_shift), N rounded up
   uint32_t nacc;            // TMEM accumulator stages (2..8): depth of the MMA <-> epilogue pipeline
   int d_nt, d_iw, d_ih, d_b; // mixed-radix digits of gridDim.x in (n_nt, n_tw, n_th, B): per-iteration tile increment
   uint32_t halo;            // ONE box per tile, taps = row-shifted views of it: 1-D taps (-d,0,+d) with d <= 64
@@ -210,9 +211,9 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   const uint32_t stage_bytes = p.halo ? p.halo_kc_bytes * (uint32_t)p.n_kc : p.a_stage_bytes + (p.w_resident ? 0u : p.b_stage_bytes);
   uint8_t* staging = smem + (size_t)p.stages * stage_bytes;
   float* bias_s = reinterpret_cast<float*>(staging + (p.tma_epi ? NUM_EPI_WARPS * p.epi_warp_bytes : 0));
-  float* asc_s = bias_s + BIAS_SMEM_FLOATS;             // act_scale / act_shift copies (TMA epilogue)
-  float* ash_s = asc_s + BIAS_SMEM_FLOATS;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(bias_s + (p.tma_epi ? 3 * BIAS_SMEM_FLOATS : 0));
+  float* asc_s = bias_s + p.bias_floats;                // act_scale / act_shift copies (TMA epilogue)
+  float* ash_s = asc_s + p.bias_floats;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(bias_s + (p.tma_epi ? 3 * p.bias_floats : 0));
   uint64_t* full = bars;
   uint64_t* empty = bars + p.stages;
   uint64_t* tmem_full = bars + 2 * p.stages;
@@ -727,7 +728,8 @@ int conv_gemm_tc(const vfx_conv_desc& d, cudaStream_t st) {
   const bool needs_ro = d.out_raw || d.residual;
   p.epi_at_off = needs_ro ? 8192u : 0u;
   p.epi_warp_bytes = p.epi_at_off + (d.out_act ? 4096u : 0u);
-  const uint32_t epi_smem = p.tma_epi ? NUM_EPI_WARPS * p.epi_warp_bytes + 3 * BIAS_SMEM_FLOATS * 4 : 0u;
+  p.bias_floats = ((uint32_t)d.N + 63u) & ~63u;
+  const uint32_t epi_smem = p.tma_epi ? NUM_EPI_WARPS * p.epi_warp_bytes + 3 * p.bias_floats * 4 : 0u;
   if (p.w_resident && p.w_bytes + epi_smem + 3 * p.a_stage_bytes > SMEM_BUDGET) { p.w_resident = 0; p.w_bytes = 0; }
   p.bw_log2 = p.tw_log2 < 5 ? p.tw_log2 : 5;
   // halo mode (resident weights): 1-D conv with taps (-d, 0, +d), d <= 64; or a 3x3 conv (taps in kh,kw order)
