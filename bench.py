@@ -158,8 +158,9 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"restore_inmem mode 0, 1 x {seconds:.1f} s synthetic utterance per step, CPU",
-                   "impl": "oracle port of voicefixer/base.py:106-139 (PyTorch fp32 CPU)"},
+        "config": {"workload": f"configs[2]: batch {args.batch} x {args.seconds:g} s synthetic degraded 44.1 kHz mono utterances per GPU, "
+                               f"mode 0, seeded synthetic checkpoints (bounded sample per step: 1 x {seconds:.1f} s utterance)",
+                   "impl": "oracle port of voicefixer/base.py:106-139 (PyTorch fp32 on the host cores)"},
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
                          "sample": f"{args.steps} x 1 x {seconds:.1f} s utterance"},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},

@@ -15,8 +15,9 @@
 //     that complete_tx on the DESTINATION CTA's mbarrier); each CTA starts its next step when its
 //     own mbarrier has received all 256 x G values.  No cluster barrier and no memory fence per
 //     step (an ncu capture of the cluster.sync() version showed 25 % membar + 12 % barrier stalls).
-//   * the G sequences of a cluster are split into two halves that ping-pong within a step, so the DSMEM
-//     exchange latency of one half hides behind the other half's matvec.
+//   * (tried: splitting the G sequences into two halves that ping-pong within a step to hide the exchange
+//     latency -- measured slower, 2.66 vs 2.23 us/step: the extra CTA barrier and mbarrier wait per
+//     half-step cost more than the latency they hide.)
 //   * fp32 FMA throughout (the recurrence is precision-sensitive); gi for step t+1 is prefetched
 //     into registers during step t.
 #include <cooperative_groups.h>
@@ -40,13 +41,10 @@ template <int G>
 __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(NT, 1)
 gru_cluster_kernel(const float* __restrict__ gi, const float* __restrict__ whh_t,
                    const float* __restrict__ bhh, int B, int T, float* __restrict__ out) {
-  // The G sequences of a cluster form two independent halves (GH each) that ping-pong through a step:
-  // while one half's new h values travel through DSMEM, the other half's matvec runs.
-  constexpr int GH = G / 2;
   extern __shared__ __align__(16) uint8_t gru_smem[];
-  float (*h_s)[2][GH][H] = reinterpret_cast<float (*)[2][GH][H]>(gru_smem);                          // [half][buf][GH][H]
-  float (*part)[KQ][GH][RPC] = reinterpret_cast<float (*)[KQ][GH][RPC]>(gru_smem + sizeof(float) * 2 * G * H);  // [half]...
-  uint64_t* hbar = reinterpret_cast<uint64_t*>(gru_smem + sizeof(float) * (2 * G * H + 2 * KQ * GH * RPC));    // [half][buf]
+  float (*h_s)[G][H] = reinterpret_cast<float (*)[G][H]>(gru_smem);                       // [2][G][H]
+  float (*part)[KQ][G][RPC] = reinterpret_cast<float (*)[KQ][G][RPC]>(gru_smem + sizeof(float) * 2 * G * H);
+  uint64_t* hbar = reinterpret_cast<uint64_t*>(gru_smem + sizeof(float) * (2 * G * H + 2 * KQ * G * RPC));
   cg::cluster_group cluster = cg::this_cluster();
   const int rank = (int)cluster.block_rank();
   const int cl = blockIdx.x / CL;
@@ -66,9 +64,10 @@ gru_cluster_kernel(const float* __restrict__ gi, const float* __restrict__ whh_t
 #pragma unroll
       for (int i = 0; i < KW; ++i) w[g3][i] = W[(long long)i * G3 + g3 * H];
   }
-  // finaliser role: thread (fg, fu) produces h'[fg][rank*32 + fu] of each half
-  const bool fin = tid < UPC * GH;
+  // finaliser role: thread (fg, fu) produces h'[fg][rank*32 + fu]
+  const bool fin = tid < UPC * G;
   const int fu = tid % UPC, fg = tid / UPC;
+  const bool fvalid = fin && (b0 + fg) < B;
   const int hu = rank * UPC + fu;
   float b_r = 0.f, b_z = 0.f, b_n = 0.f;
   if (fin) {
@@ -78,7 +77,7 @@ gru_cluster_kernel(const float* __restrict__ gi, const float* __restrict__ whh_t
   // shared::cluster addresses of every replica's h buffer and mbarriers
   uint32_t rem_h[CL], rem_bar[CL];
   {
-    const uint32_t lh = (uint32_t)__cvta_generic_to_shared(&h_s[0][0][0][0]);
+    const uint32_t lh = (uint32_t)__cvta_generic_to_shared(&h_s[0][0][0]);
     const uint32_t lb = (uint32_t)__cvta_generic_to_shared(&hbar[0]);
 #pragma unroll
     for (int c = 0; c < CL; ++c) {
@@ -86,10 +85,11 @@ gru_cluster_kernel(const float* __restrict__ gi, const float* __restrict__ whh_t
       asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(rem_bar[c]) : "r"(lb), "r"(c));
     }
   }
-  for (int i = tid; i < 2 * G * H; i += NT) (&h_s[0][0][0][0])[i] = 0.f;
+  for (int i = tid; i < 2 * G * H; i += NT) (&h_s[0][0][0])[i] = 0.f;
   if (tid == 0) {
     const uint32_t lb = (uint32_t)__cvta_generic_to_shared(&hbar[0]);
-    for (int i = 0; i < 4; ++i) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(lb + 8u * i));
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(lb));
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(lb + 8));
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   cluster.sync();
@@ -97,100 +97,86 @@ gru_cluster_kernel(const float* __restrict__ gi, const float* __restrict__ whh_t
   // input projections are prefetched two steps ahead (register ring): an HBM round trip is longer
   // than one step
   const long long gstride = 2LL * G3;                     // floats per (b, t)
-  const float* gbase[2];
-  bool fvalid[2];
-  float pr[2][2], pz[2][2], pn[2][2];
+  const float* gbase = gi + ((long long)(b0 + fg) * T) * gstride + dir * G3 + hu;
+  float pr[2] = {0.f, 0.f}, pz[2] = {0.f, 0.f}, pn[2] = {0.f, 0.f};
 #pragma unroll
-  for (int hf = 0; hf < 2; ++hf) {
-    const int bi = b0 + hf * GH + fg;
-    fvalid[hf] = fin && bi < B;
-    gbase[hf] = gi + ((long long)bi * T) * gstride + dir * G3 + hu;
-#pragma unroll
-    for (int s = 0; s < 2; ++s) {
-      pr[hf][s] = pz[hf][s] = pn[hf][s] = 0.f;
-      if (fvalid[hf] && s < T) {
-        const int ts = dir == 0 ? s : T - 1 - s;
-        const float* p = gbase[hf] + (long long)ts * gstride;
-        pr[hf][s] = p[0]; pz[hf][s] = p[H]; pn[hf][s] = p[2 * H];
-      }
+  for (int s = 0; s < 2; ++s)
+    if (fvalid && s < T) {
+      const int ts = dir == 0 ? s : T - 1 - s;
+      const float* p = gbase + (long long)ts * gstride;
+      pr[s] = p[0]; pz[s] = p[H]; pn[s] = p[2 * H];
     }
-  }
 
   for (int step = 0; step < T; ++step) {
     const int t = dir == 0 ? step : T - 1 - step;
     const int cur = step & 1, nxt = cur ^ 1;
     const bool last = step + 1 == T;
+    if (tid == 0 && !last) {      // arm the mbarrier of the buffer this step's exchange fills
+      const uint32_t lb = (uint32_t)__cvta_generic_to_shared(&hbar[nxt]);
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(lb), "r"(G * H * 4) : "memory");
+    }
+    const float gir = pr[0], giz = pz[0], gin = pn[0];
+    pr[0] = pr[1]; pz[0] = pz[1]; pn[0] = pn[1];
+    if (fvalid && step + 2 < T) {
+      const int tn = dir == 0 ? t + 2 : t - 2;
+      const float* p = gbase + (long long)tn * gstride;
+      pr[1] = p[0]; pz[1] = p[H]; pn[1] = p[2 * H];
+    }
+    // ---- phase A: partial dot products over this thread's K quarter, all G sequences
+    float acc[3][G];
 #pragma unroll
-    for (int hf = 0; hf < 2; ++hf) {
-      if (tid == 0 && !last) {      // arm the mbarrier of the buffer this step's exchange of this half fills
-        const uint32_t lb = (uint32_t)__cvta_generic_to_shared(&hbar[hf * 2 + nxt]);
-        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(lb), "r"(GH * H * 4) : "memory");
-      }
-      if (step > 0) {               // h[cur] of this half: sent during the previous step, one half-step ago
-        const uint32_t lb = (uint32_t)__cvta_generic_to_shared(&hbar[hf * 2 + cur]);
-        const uint32_t parity = (uint32_t)(((step - 1) >> 1) & 1);
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "GRU_WAIT:\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-            "@p bra GRU_DONE;\n\t"
-            "bra GRU_WAIT;\n\t"
-            "GRU_DONE:\n\t}" ::"r"(lb), "r"(parity) : "memory");
-      }
-      const float gir = pr[hf][0], giz = pz[hf][0], gin = pn[hf][0];
-      pr[hf][0] = pr[hf][1]; pz[hf][0] = pz[hf][1]; pn[hf][0] = pn[hf][1];
-      if (fvalid[hf] && step + 2 < T) {
-        const int tn = dir == 0 ? t + 2 : t - 2;
-        const float* p = gbase[hf] + (long long)tn * gstride;
-        pr[hf][1] = p[0]; pz[hf][1] = p[H]; pn[hf][1] = p[2 * H];
-      }
-      // ---- phase A: partial dot products over this thread's K slice, the GH sequences of this half
-      float acc[3][GH];
+    for (int g3 = 0; g3 < 3; ++g3)
 #pragma unroll
-      for (int g3 = 0; g3 < 3; ++g3)
+      for (int g = 0; g < G; ++g) acc[g3][g] = 0.f;
 #pragma unroll
-        for (int g = 0; g < GH; ++g) acc[g3][g] = 0.f;
+    for (int i = 0; i < KW; i += 4) {
 #pragma unroll
-      for (int i = 0; i < KW; i += 4) {
+      for (int g = 0; g < G; ++g) {
+        const float4 hv = *reinterpret_cast<const float4*>(&h_s[cur][g][q * KW + i]);
 #pragma unroll
-        for (int g = 0; g < GH; ++g) {
-          const float4 hv = *reinterpret_cast<const float4*>(&h_s[hf][cur][g][q * KW + i]);
-#pragma unroll
-          for (int g3 = 0; g3 < 3; ++g3) {
-            acc[g3][g] = fmaf(w[g3][i], hv.x, acc[g3][g]);
-            acc[g3][g] = fmaf(w[g3][i + 1], hv.y, acc[g3][g]);
-            acc[g3][g] = fmaf(w[g3][i + 2], hv.z, acc[g3][g]);
-            acc[g3][g] = fmaf(w[g3][i + 3], hv.w, acc[g3][g]);
-          }
+        for (int g3 = 0; g3 < 3; ++g3) {
+          acc[g3][g] = fmaf(w[g3][i], hv.x, acc[g3][g]);
+          acc[g3][g] = fmaf(w[g3][i + 1], hv.y, acc[g3][g]);
+          acc[g3][g] = fmaf(w[g3][i + 2], hv.z, acc[g3][g]);
+          acc[g3][g] = fmaf(w[g3][i + 3], hv.w, acc[g3][g]);
         }
       }
+    }
 #pragma unroll
-      for (int g3 = 0; g3 < 3; ++g3)
+    for (int g3 = 0; g3 < 3; ++g3)
 #pragma unroll
-        for (int g = 0; g < GH; ++g) part[hf][q][g][g3 * UPC + u] = acc[g3][g];
-      __syncthreads();
-      // ---- phase B: gates for 32 units x GH sequences, push h' into all 8 replicas
-      if (fin) {
-        float gr = b_r, gz = b_z, gn = b_n;
+      for (int g = 0; g < G; ++g) part[cur][q][g][g3 * UPC + u] = acc[g3][g];
+    __syncthreads();
+    // ---- phase B: gates for 32 units x G sequences, push h' into all 8 replicas
+    if (fin) {
+      float gr = b_r, gz = b_z, gn = b_n;
 #pragma unroll
-        for (int k = 0; k < KQ; ++k) {
-          gr += part[hf][k][fg][fu]; gz += part[hf][k][fg][UPC + fu]; gn += part[hf][k][fg][2 * UPC + fu];
-        }
-        const float rg = 1.f / (1.f + expf(-(gir + gr)));
-        const float zg = 1.f / (1.f + expf(-(giz + gz)));
-        const float ng = tanhf(gin + rg * gn);
-        const float hn = (1.f - zg) * ng + zg * h_s[hf][cur][fg][hu];
-        if (!last) {
-          const uint32_t off = (uint32_t)((((hf * 2 + nxt) * GH + fg) * H + hu) * 4);
-#pragma unroll
-          for (int c = 0; c < CL; ++c)
-            asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];"
-                         ::"r"(rem_h[c] + off), "r"(__float_as_uint(hn)), "r"(rem_bar[c] + 8u * (hf * 2 + nxt)) : "memory");
-        }
-        if (fvalid[hf]) out[((long long)(b0 + hf * GH + fg) * T + t) * (2 * H) + dir * H + hu] = hn;
+      for (int k = 0; k < KQ; ++k) {
+        gr += part[cur][k][fg][fu]; gz += part[cur][k][fg][UPC + fu]; gn += part[cur][k][fg][2 * UPC + fu];
       }
-      // `part[hf]` is rewritten only in the next step's phase A of this half: the other half's
-      // __syncthreads lies in between, so one barrier per half-step suffices.
+      const float rg = 1.f / (1.f + expf(-(gir + gr)));
+      const float zg = 1.f / (1.f + expf(-(giz + gz)));
+      const float ng = tanhf(gin + rg * gn);
+      const float hn = (1.f - zg) * ng + zg * h_s[cur][fg][hu];
+      if (!last) {
+        const uint32_t off = (uint32_t)(((nxt * G + fg) * H + hu) * 4);
+#pragma unroll
+        for (int c = 0; c < CL; ++c)
+          asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];"
+                       ::"r"(rem_h[c] + off), "r"(__float_as_uint(hn)), "r"(rem_bar[c] + 8u * nxt) : "memory");
+      }
+      if (fvalid) out[((long long)(b0 + fg) * T + t) * (2 * H) + dir * H + hu] = hn;
+    }
+    if (!last) {                  // wait until all 8 CTAs' contributions to h[nxt] have landed here
+      const uint32_t lb = (uint32_t)__cvta_generic_to_shared(&hbar[nxt]);
+      const uint32_t parity = (uint32_t)((step >> 1) & 1);
+      asm volatile(
+          "{\n\t.reg .pred p;\n\t"
+          "GRU_WAIT:\n\t"
+          "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+          "@p bra GRU_DONE;\n\t"
+          "bra GRU_WAIT;\n\t"
+          "GRU_DONE:\n\t}" ::"r"(lb), "r"(parity) : "memory");
     }
   }
   cluster.sync();   // no CTA may exit while a peer could still address its shared memory
@@ -199,7 +185,7 @@ gru_cluster_kernel(const float* __restrict__ gi, const float* __restrict__ whh_t
 template <int G>
 int launch(const float* gi, const float* whh_t, const float* bhh, int B, int T, float* out, cudaStream_t st) {
   const int groups = (B + G - 1) / G;
-  const size_t smem = sizeof(float) * (2 * G * H + 2 * KQ * (G / 2) * RPC) + 4 * 8 + 16;
+  const size_t smem = sizeof(float) * (2 * G * H + 2 * KQ * G * RPC) + 16;
   static bool attr_set = false;
   if (!attr_set) {
     VFX_CUDA_CHECK(cudaFuncSetAttribute(gru_cluster_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
