@@ -121,12 +121,23 @@ __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::
 __device__ __forceinline__ void tc_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-__device__ __forceinline__ void tc_mma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+// Lean issue form: the descriptor high word (SBO, version, layout) is constant for the kernel; per MMA only
+// the 32-bit low words (start address >> 4, LBO field = 1) change.  lo = desc_lo(addr) is one shift/or and
+// advancing K by 16 elements is lo + 2.
+__device__ __forceinline__ uint32_t desc_lo(uint32_t saddr) { return ((saddr >> 4) & 0x3FFFu) | (1u << 16); }
+__device__ __forceinline__ uint32_t desc_hi(uint32_t sbo16, uint32_t layout_type) {
+  return (sbo16 & 0x3FFFu) | (1u << 14) | ((layout_type & 7u) << 29);
+}
+template <bool ACCUM>
+__device__ __forceinline__ void tc_mma_lo(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t hi, uint32_t idesc) {
+  if (ACCUM)
+    asm volatile("{\n\t.reg .b64 da, db;\n\t.reg .pred p;\n\tsetp.eq.b32 p, 0, 0;\n\tmov.b64 da, {%1, %3};\n\tmov.b64 db, {%2, %3};\n\t"
+                 "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n\t}"
+                 ::"r"(d_tmem), "r"(a_lo), "r"(b_lo), "r"(hi), "r"(idesc) : "memory");
+  else
+    asm volatile("{\n\t.reg .b64 da, db;\n\t.reg .pred p;\n\tsetp.ne.b32 p, 0, 0;\n\tmov.b64 da, {%1, %3};\n\tmov.b64 db, {%2, %3};\n\t"
+                 "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n\t}"
+                 ::"r"(d_tmem), "r"(a_lo), "r"(b_lo), "r"(hi), "r"(idesc) : "memory");
 }
 __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t* v) {
   asm volatile(
@@ -143,16 +154,7 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t* v) {
 
 // K-major swizzled shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout):
 // [0,14) start>>4, [16,30) LBO>>4 (unused for swizzled K-major: 1), [32,46) SBO>>4, [46,48) version=1,
-// [61,64) layout type.
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t sbo16, uint32_t layout_type) {
-  uint64_t d = 0;
-  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
-  d |= (uint64_t)1 << 16;
-  d |= (uint64_t)(sbo16 & 0x3FFF) << 32;
-  d |= (uint64_t)1 << 46;
-  d |= (uint64_t)(layout_type & 7) << 61;
-  return d;
-}
+// [61,64) layout type -- built as desc_lo()/desc_hi() below.
 // Row-shifted views of a SWIZZLE_128B tile (halo mode) use the same descriptor with the shifted start
 // address and base_offset 0: verified on B200 that the MMA unit, like TMA, derives the swizzle phase
 // from the absolute shared-memory address bits [7,10) (base_offset = (addr>>7)&7 gives wrong results).
@@ -345,18 +347,36 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           const uint32_t d_tmem = tmem_base + (i & nacc_mask) * p.Ntile;
           const uint32_t s_addr = smem_u32(smem + (size_t)s * stage_bytes);
           const uint32_t w_addr = smem_u32(wres);
+          const uint32_t dhi = desc_hi(p.sbo16, p.layout_type);
           if (elect_one()) {
+            // ntaps is 3 (1-D) or 9 (3x3): bodies of 3 taps x kk MMAs are unrolled so that the descriptor
+            // arithmetic and the moves into uniform registers of several MMAs overlap (a fully rolled loop
+            // serialised ~200 cycles per MMA and made this warp the bottleneck of the N=32 UNet layers)
 #pragma unroll 1
-            for (int tap = 0; tap < p.ntaps; ++tap) {
+            for (int tap0 = 0; tap0 < p.ntaps; tap0 += 3) {
 #pragma unroll 1
               for (int kc = 0; kc < p.n_kc; ++kc) {
-                const uint32_t a_addr = s_addr + (uint32_t)kc * p.halo_kc_bytes + p.halo_off[tap] * (uint32_t)(p.KC * 2);
-                const uint32_t b_addr = w_addr + (uint32_t)(tap * p.n_kc + kc) * p.b_stage_bytes;
-#pragma unroll 1
-                for (int k = 0; k < kk; ++k) {
-                  const uint64_t ad = make_smem_desc(a_addr + k * 32, p.sbo16, p.layout_type);
-                  const uint64_t bd = make_smem_desc(b_addr + k * 32, p.sbo16, p.layout_type);
-                  tc_mma_bf16(d_tmem, ad, bd, p.idesc, (tap | kc | k) ? 1u : 0u);
+                uint32_t a_lo[3], b_lo[3];
+#pragma unroll
+                for (int dt = 0; dt < 3; ++dt) {
+                  a_lo[dt] = desc_lo(s_addr + (uint32_t)kc * p.halo_kc_bytes + p.halo_off[tap0 + dt] * (uint32_t)(p.KC * 2));
+                  b_lo[dt] = desc_lo(w_addr + (uint32_t)((tap0 + dt) * p.n_kc + kc) * p.b_stage_bytes);
+                }
+                if ((tap0 | kc) == 0) tc_mma_lo<false>(d_tmem, a_lo[0], b_lo[0], dhi, p.idesc);   // first MMA of the tile overwrites
+                else tc_mma_lo<true>(d_tmem, a_lo[0], b_lo[0], dhi, p.idesc);
+                if (kk == 4) {
+#pragma unroll
+                  for (int k = 1; k < 4; ++k) tc_mma_lo<true>(d_tmem, a_lo[0] + 2 * k, b_lo[0] + 2 * k, dhi, p.idesc);
+#pragma unroll
+                  for (int dt = 1; dt < 3; ++dt)
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) tc_mma_lo<true>(d_tmem, a_lo[dt] + 2 * k, b_lo[dt] + 2 * k, dhi, p.idesc);
+                } else {
+                  tc_mma_lo<true>(d_tmem, a_lo[0] + 2, b_lo[0] + 2, dhi, p.idesc);
+#pragma unroll
+                  for (int dt = 1; dt < 3; ++dt)
+#pragma unroll
+                    for (int k = 0; k < 2; ++k) tc_mma_lo<true>(d_tmem, a_lo[dt] + 2 * k, b_lo[dt] + 2 * k, dhi, p.idesc);
                 }
               }
             }
@@ -385,11 +405,13 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             const uint32_t b_addr = p.w_resident ? smem_u32(wres + (size_t)ks * p.b_stage_bytes) : a_addr + p.a_stage_bytes;
             const long long tm0 = dbg ? clock64() : 0;
             if (elect_one()) {
-#pragma unroll 4
-              for (int k = 0; k < kk; ++k) {
-                const uint64_t ad = make_smem_desc(a_addr + k * 32, p.sbo16, p.layout_type);
-                const uint64_t bd = make_smem_desc(b_addr + k * 32, p.sbo16, p.layout_type);
-                tc_mma_bf16(d_tmem, ad, bd, p.idesc, (ks | k) ? 1u : 0u);
+              const uint32_t ghi = desc_hi(p.sbo16, p.layout_type), ga = desc_lo(a_addr), gb = desc_lo(b_addr);
+              if (ks == 0) tc_mma_lo<false>(d_tmem, ga, gb, ghi, p.idesc);
+              else tc_mma_lo<true>(d_tmem, ga, gb, ghi, p.idesc);
+              tc_mma_lo<true>(d_tmem, ga + 2, gb + 2, ghi, p.idesc);
+              if (kk == 4) {
+                tc_mma_lo<true>(d_tmem, ga + 4, gb + 4, ghi, p.idesc);
+                tc_mma_lo<true>(d_tmem, ga + 6, gb + 6, ghi, p.idesc);
               }
               tc_commit(&empty[s]);                   // frees the smem stage when these MMAs retire
               if (ks == k_steps - 1) tc_commit(&tmem_full[(i0 + j) & nacc_mask]);   // accumulator ready for the epilogue
