@@ -61,6 +61,7 @@ struct TcParams {
   int d_nt, d_iw, d_ih, d_b; // mixed-radix digits of gridDim.x in (n_nt, n_tw, n_th, B): per-iteration tile increment
   uint32_t halo;            // ONE box per tile, taps = row-shifted views of it: 1-D taps (-d,0,+d) with d <= 64
                             // [(128+2d) rows], or 3x3 [(th+2) x tw rows starting at (w0-1, h0-1)]
+  uint32_t halo_boxes;                 // 1 = one halo box per K chunk; ntaps = one 128-row box per tap (multi-box tile stage)
   uint32_t halo_rows, halo_kc_bytes;   // rows of the TMA box, bytes of one K-chunk block (rows rounded up + zero pad rows)
   int halo_pw, halo_ph;                // the box starts at (w0 - pw, h0 - ph)
   uint32_t halo_off[9];                // row offset of each tap's 128-row view inside the box
@@ -287,10 +288,18 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           mbar_wait_t(&empty[s], ph ^ 1, w_empty, dbg);
           uint8_t* sa = smem + (size_t)s * stage_bytes;
           if (elect_one()) {
-            mbar_expect_tx(&full[s], p.halo_rows * (uint32_t)(p.KC * 2) * (uint32_t)p.n_kc);
+            mbar_expect_tx(&full[s], p.halo_rows * (uint32_t)(p.KC * 2) * (uint32_t)p.n_kc * p.halo_boxes);
 #pragma unroll 1
-            for (int kc = 0; kc < p.n_kc; ++kc)
-              tma_load_4d(&tmA, &full[s], sa + (size_t)kc * p.halo_kc_bytes, kc * p.KC, t.w0 - p.halo_pw, t.h0 - p.halo_ph, t.b);
+            for (int kc = 0; kc < p.n_kc; ++kc) {
+              if (p.halo_boxes == 1) {
+                tma_load_4d(&tmA, &full[s], sa + (size_t)kc * p.halo_kc_bytes, kc * p.KC, t.w0 - p.halo_pw, t.h0 - p.halo_ph, t.b);
+              } else {      // one aligned 128-row box per tap, all on this stage's barrier
+#pragma unroll 1
+                for (int tap = 0; tap < p.ntaps; ++tap)
+                  tma_load_4d(&tmA, &full[s], sa + (size_t)kc * p.halo_kc_bytes + (size_t)p.halo_off[tap] * (p.KC * 2), kc * p.KC,
+                              t.w0 + p.dw[tap], t.h0 + p.dh[tap], t.b);
+              }
+            }
           }
           __syncwarp();
           if (++s == (uint32_t)p.stages) { s = 0; ph ^= 1; }
@@ -776,9 +785,17 @@ int conv_gemm_tc(const vfx_conv_desc& d, cudaStream_t st) {
       }
       box_w = (uint32_t)tw; box_h = (uint32_t)th + 2; p.halo_pw = 1; p.halo_ph = 1; extra = 2;
     }
+    p.halo_boxes = 1;
+    if (!ok && d.H == 1 && d.Hq == 1 && d.ntaps == 3 && tw == TILE_M && KC == 64) {
+      // large dilation: the taps' boxes do not overlap -> one aligned 128-row box per tap, but still ONE pipeline
+      // stage / barrier round trip per tile
+      box_w = TILE_M; box_h = 1; p.halo_pw = 0; p.halo_ph = 0; p.halo_boxes = 3;
+      for (int t = 0; t < 3; ++t) p.halo_off[t] = (uint32_t)(t * TILE_M);
+      ok = true;
+    }
     if (ok) {
       p.halo_rows = box_w * box_h;
-      p.halo_kc_bytes = ((p.halo_rows + extra + 7) / 8) * 8 * row_b;
+      p.halo_kc_bytes = ((p.halo_rows * p.halo_boxes + extra + 7) / 8) * 8 * row_b;
       p.halo_kc_bytes = (p.halo_kc_bytes + 1023) / 1024 * 1024;
       // worth it only if at least 2 tiles can be in flight
       p.halo = ((uint32_t)SMEM_BUDGET - p.w_bytes - epi_smem) / (p.halo_kc_bytes * (uint32_t)p.n_kc) >= 2 ? 1u : 0u;
