@@ -168,3 +168,31 @@ def test_cuda_graph_replay_matches_direct_launch(engine_bf16):
     g.replay()
     torch.cuda.synchronize()
     assert torch.equal(out, ref)
+
+
+def test_api_modes_1_2_and_vocoder_oracle(tmp_path, monkeypatch, states):
+    """restore_inmem modes 1 / 2 and Vocoder.oracle through the mirrored API, against the oracle."""
+    from voicefixer_b200 import synthetic, api, wavio
+    from oracle import vf_oracle as O
+    monkeypatch.setenv("HOME", str(tmp_path))
+    synthetic.write_checkpoints(str(tmp_path), seed=0)
+    vf = api.VoiceFixer(precision="fp32")
+    wav = synthetic.make_utterances(1, seconds=0.6, seed=51)[0]
+    out1 = vf.restore_inmem(wav, cuda=True, mode=1)                         # mode 1: pre-filter, shorter output
+    ref1 = O.restore_inmem(wav, states[0], states[1], mode=1)
+    assert out1.shape == ref1.shape == (1, 512 * (wav.shape[0] // 512))
+    assert rel_rms(out1, ref1) < TOL_WAV
+    out2 = vf.restore_inmem(wav, cuda=True, mode=2)                         # mode 2: train-mode BN, no dropout masks given
+    ref2 = O.restore_inmem(wav, states[0], states[1], mode=2)
+    assert out2.shape == (1, wav.shape[0]) and rel_rms(out2, ref2) < 5e-4
+    with pytest.raises(ValueError):
+        vf.restore_inmem(wav, cuda=True, mode=3)
+    # Vocoder.oracle: wav file -> |STFT| -> Slaney mel -> Generator -> int16 wav file (vocoder/base.py:58-77)
+    src = synthetic.make_utterances(1, seconds=0.4, seed=52)[0]
+    wavio.save_wave(src[None], str(tmp_path / "src.wav"))
+    voc = api.Vocoder(44100, _engine=vf._engine)
+    voc.oracle(str(tmp_path / "src.wav"), str(tmp_path / "orc.wav"), cuda=True)
+    got = wavio.load_mono(str(tmp_path / "orc.wav"))
+    x16 = wavio.load_mono(str(tmp_path / "src.wav"))                         # what oracle() actually read (int16 round trip)
+    ref = O.oracle_wave(x16, states[1])[0, 0] / 2 ** 15
+    assert got.shape == ref.shape and float(np.mean(np.abs(got - ref))) < 2e-4
