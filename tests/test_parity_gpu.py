@@ -170,6 +170,7 @@ def test_cuda_graph_replay_matches_direct_launch(engine_bf16):
     assert torch.equal(out, ref)
 
 
+@pytest.mark.timeout(240)
 def test_api_modes_1_2_and_vocoder_oracle(tmp_path, monkeypatch, states):
     """restore_inmem modes 1 / 2 and Vocoder.oracle through the mirrored API, against the oracle."""
     from voicefixer_b200 import synthetic, api, wavio
@@ -181,10 +182,17 @@ def test_api_modes_1_2_and_vocoder_oracle(tmp_path, monkeypatch, states):
     out1 = vf.restore_inmem(wav, cuda=True, mode=1)                         # mode 1: pre-filter, shorter output
     ref1 = O.restore_inmem(wav, states[0], states[1], mode=1)
     assert out1.shape == ref1.shape == (1, 512 * (wav.shape[0] // 512))
-    assert rel_rms(out1, ref1) < TOL_WAV
-    out2 = vf.restore_inmem(wav, cuda=True, mode=2)                         # mode 2: train-mode BN, no dropout masks given
-    ref2 = O.restore_inmem(wav, states[0], states[1], mode=2)
-    assert out2.shape == (1, wav.shape[0]) and rel_rms(out2, ref2) < 5e-4
+    # mode 1 tolerance 1e-3: the fp32 rFFT -> irFFT round trip of the pre-filter differs from numpy's by ~4e-5 on a
+    # noisy input (cut bins identical), which the network amplifies ~6x; with the oracle's filtered input the
+    # restore matches to 4e-6 (tools/dbg_mode1.py)
+    assert rel_rms(out1, ref1) < 1e-3
+    # mode 2 (train-mode BN, no dropout masks): <= 64 frames is an error in the reference too (1x1 UNet centre)
+    with pytest.raises(ValueError, match="more than 1 value per channel"):
+        vf.restore_inmem(wav, cuda=True, mode=2)
+    wav2 = synthetic.make_utterances(1, seconds=1.6, seed=53)[0]
+    out2 = vf.restore_inmem(wav2, cuda=True, mode=2)
+    ref2 = O.restore_inmem(wav2, states[0], states[1], mode=2)
+    assert out2.shape == (1, wav2.shape[0]) and rel_rms(out2, ref2) < 5e-4
     with pytest.raises(ValueError):
         vf.restore_inmem(wav, cuda=True, mode=3)
     # Vocoder.oracle: wav file -> |STFT| -> Slaney mel -> Generator -> int16 wav file (vocoder/base.py:58-77)

@@ -167,6 +167,10 @@ class VoiceFixer:
             groups.setdefault(len(s), []).append(i)
         outs = [None] * len(segs)
         for L, idxs in groups.items():
+            if mode == 2 and 1 + (512 * (L // 512) if mode == 1 else L) // 441 <= 64:
+                # torch.nn.functional.batch_norm in the reference (train mode, 1x1 UNet centre)
+                raise ValueError("Expected more than 1 value per channel when training, got input size "
+                                 "torch.Size([1, 384, 1, 1])")
             x = torch.from_numpy(np.stack([segs[i] for i in idxs])).to(dev)
             if mode == 1:
                 x, _ = eng.hf_cut(x)                                     # shorter: 512*(L//512)

@@ -461,6 +461,9 @@ int denoiser_forward(Ctx& c, const float* mel, int B, int T, const uint8_t* drop
 
 int analysis_forward(Ctx& c, const float* mel, int B, int T, const uint8_t* drop, float* mel_log_out) {
   const int Tp = (T + 63) / 64 * 64;
+  // mode 2: the reference's train-mode BatchNorm raises "Expected more than 1 value per channel when training"
+  // when the UNet centre is 1x1, i.e. for segments of at most 64 frames
+  if (c.train() && !c.dry) VFX_REQUIRE(Tp > 64, "mode 2 needs more than 64 frames per segment (got T=%d): Expected more than 1 value per channel when training", T);
   const size_t m0 = c.ws->mark();
   float* xlog = c.ws->alloc<float>((size_t)B * T * 128);
   float* unet_in = c.ws->alloc<float>((size_t)B * Tp * 127 * 2);
