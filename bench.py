@@ -167,12 +167,69 @@ def run_reference(args):
     }))
 
 
+def run_torch_gpu(args):
+    """Library baseline: the reference's op sequence (oracle restatement: F.conv1d/conv2d/conv_transpose, batch_norm,
+    matmul-based GRU loop) executed by stock PyTorch on cuda:0 with its defaults (TF32 convolutions through cuDNN).
+    Reported for context only; none of this repo's kernels run here."""
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    from voicefixer_b200 import synthetic
+    from oracle import vf_oracle as O
+    dev = "cuda:0"
+    B = min(args.batch, 8)                              # fp32 NCHW activations of the reference layout: 8 items ~ 25 GB peak
+    ana = {k: v.to(dev) for k, v in synthetic.make_analysis_state(0).items()}
+    voc = {k: v.to(dev) for k, v in synthetic.make_vocoder_state(1).items()}
+    O.mel_weight = (lambda f: (lambda: f().to(dev)))(O.mel_weight)
+    # the oracle's explicit Python GRU loop would be unfair to PyTorch: use cuDNN's nn.GRU like the reference does
+    grus = {}
+    for g in ("7", "8"):
+        m = torch.nn.GRU(512, 256, num_layers=2, bidirectional=True, batch_first=True).to(dev)
+        pre = f"generator.denoiser.{g}.gru."
+        m.load_state_dict({k[len(pre):]: v for k, v in ana.items() if k.startswith(pre)})
+        grus[f"generator.denoiser.{g}"] = m.eval()
+
+    def bn_gru_cudnn(x, ana_, prefix, train):
+        x = O._bn1(x, ana_, prefix + ".bn", train).squeeze(1)
+        return grus[prefix](x)[0].unsqueeze(1)
+    O.bn_gru = bn_gru_cudnn
+    wav = torch.from_numpy(synthetic.make_utterances(min(B, 4), seconds=args.seconds, seed=1234)).repeat((B + 3) // 4, 1)[:B].to(dev)
+
+    @torch.no_grad()
+    def step():
+        _, mel = O.frontend(wav, ana)
+        out_mel = O.analysis(mel, ana)
+        S = torch.abs(O.from_log(out_mel) / O.mel_weight()[None, None, None, :])
+        S = 20 * torch.log10(torch.clamp(S, min=1e-5)) - 20.0
+        S = torch.clip(8.0 * ((S + 115.0) / 115.0) - 4.0, -4.0, 4.0)[:, 0].transpose(1, 2)
+        cond = torch.cat([S, torch.full((S.shape[0], 128, S.shape[-1] % 2 + 4), -4.0, device=dev)], -1)
+        return O.trim_center(O.vocoder_generator(cond, voc), wav.shape[-1])
+
+    for _ in range(max(1, min(args.warmup, 2))):
+        step()
+    torch.cuda.synchronize()
+    steps = max(1, min(args.steps, 3))
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        step()
+    e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    v = B * args.seconds / (ms * 1e-3)
+    print(json.dumps({"impl": "torch-gpu", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": 1, "steps": steps,
+                      "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "dtype": "tf32/fp32 (torch defaults)",
+                      "data": "synthetic",
+                      "config": {"workload": f"batch {B} x {args.seconds:g} s, mode 0, PyTorch {torch.__version__} ops on cuda:0 "
+                                             "(cuDNN convs/GRU, cuBLAS)", "note": "library baseline, context only"}}))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference", "torch-gpu"],
+                    help="b200: this repo; reference: the reference's CPU path (oracle port); torch-gpu: the same PyTorch "
+                         "ops on the GPU through cuDNN/cuBLAS (library baseline, what the reference's cuda=True path runs)")
     ap.add_argument("--batch", type=int, default=32, help="utterances per GPU")
     ap.add_argument("--seconds", type=float, default=10.0)
     ap.add_argument("--precision", default=os.environ.get("VFX_PRECISION", "bf16"),
@@ -182,6 +239,8 @@ def main():
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
+    if args.impl == "torch-gpu":
+        return run_torch_gpu(args)
     args.warmup = max(args.warmup, 3)
 
     import torch.distributed as dist
