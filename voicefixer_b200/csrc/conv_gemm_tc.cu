@@ -2,20 +2,29 @@
 // TMA-staged bf16 tiles -> tcgen05.mma (fp32 accumulators in TMEM) -> fused epilogue.
 //
 // Same contract as conv_gemm_simt (vfx_conv_desc); this is the production path behind the
-// reference's Conv1d/Conv2d/ConvTranspose layers (see conv_gemm_simt.cu for the file:line list).
+// reference's Conv1d / Conv2d / ConvTranspose / Linear layers (file:line list in conv_gemm_simt.cu).
 //
 //   D[128 positions][Ntile channels] += A_tap[128][KC] * W_tap[Ntile][KC]^T     (K-major, SW128/SW64)
 //
-// * One M-tile = a (th x tw) patch of the output grid of one item, th*tw = 128.  Every tap is a
-//   TMA box load of the same patch shifted by (dh, dw); rows/columns outside the tensor are
-//   zero-filled by TMA, which IS the convolution's zero padding (no im2col, no halo logic).
-// * Persistent CTAs (one per SM), static round-robin tile schedule, warp roles:
-//     warp 0   TMA producer (one elected lane)        warp 1   tcgen05.mma issuer (one lane)
-//     warp 2-9 epilogue: tcgen05.ld TMEM->registers, +bias, +residual(fp32), activation, stores
-//              (8 warps: sub-partition = warp%4, column chunks split even/odd between the pair;
-//               residual rows are prefetched before the accumulator wait and one chunk ahead)
-//   smem ring of S stages (full/empty mbarriers) and up to 8 TMEM accumulator stages (512 columns /
-//   Ntile; tmem_full/empty) so the MMA -> epilogue -> MMA latency chain is pipelined several tiles deep.
+// * One M-tile = a (th x tw) patch of the output grid of one item, th*tw = 128.  Operand staging:
+//     generic   every tap is a TMA box of the patch shifted by (dh, dw); rows/columns outside the
+//               tensor are zero-filled by TMA = the convolution's zero padding (no im2col).
+//     halo      (weights resident) ONE box per tile -- 1-D taps (-d,0,+d), d <= 64: (128+2d) rows;
+//               3x3: (th+2) x tw rows from (w0-1, h0-1) -- every tap is a row-shifted descriptor view
+//               of it (the MMA unit swizzles on absolute smem address bits, base_offset stays 0).
+//     multi-box (1-D, large dilation) one aligned 128-row box per tap, all on one stage / barrier.
+//   Weights are TMA boxes [Ntile][KC]; if all taps fit (<= 100 KB, one N tile) they stay resident.
+// * Persistent CTAs (one per SM), static round-robin tiles (division-free digit iterator), roles:
+//     warp 0   TMA producer  } warp-uniform loops, elect.sync around the issue instructions so that
+//     warp 1   MMA issuer    } descriptors live in uniform registers (no R2UR waterfalls)
+//     warp 2-9 epilogue (sub-partition = warp%4; column chunks split even/odd between the pair):
+//              TMA-staged for plain stride-1 outputs (residual tile in by TMA, fp32 result written back
+//              in place + activated bf16 operand tile, TMA stores), direct 16-byte stores otherwise;
+//              optional per-channel affine before the activation (fused eval-mode BatchNorm).
+//   smem ring of up to 24 stages (full/empty mbarriers), up to 8 TMEM accumulator stages (512 columns /
+//   Ntile; tmem_full/empty).
+// * Diagnostics: VFX_TC_DEBUG=1 prints per-role cycle counters (time in each wait / issue section) for
+//   three CTAs after every launch; VFX_NO_HALO / VFX_NO_TMA_EPI disable the respective paths.
 #include <cuda.h>
 #include <stdlib.h>
 #include <vector>
@@ -30,7 +39,7 @@ constexpr int NUM_EPI_WARPS = 8;          // two per TMEM sub-partition, interle
 constexpr int NUM_THREADS = 64 + 32 * NUM_EPI_WARPS;
 constexpr int SMEM_BUDGET = 216 * 1024;                   // weights + stages + epilogue staging (227 KB max incl. barriers/alignment)
 constexpr int MAX_STAGES = 24;
-constexpr int BIAS_SMEM_FLOATS = 2048;                   // TMA epilogue keeps bias[0..bias_mod) in smem
+constexpr int BIAS_SMEM_FLOATS = 2048;                   // TMA epilogue: max N whose bias / affine arrays are kept in smem
 
 struct TcParams {
   // tile schedule
