@@ -162,3 +162,40 @@ def test_cli_job_planning_matches_reference_naming(tmp_path):
         plan_jobs(build_parser().parse_args(["-i", str(tmp_path / "in" / "a.wav"), "-o", "x.flac"]))
     with pytest.raises(ValueError, match="only support the .wav"):
         plan_jobs(build_parser().parse_args(["-i", str(tmp_path / "in" / "c.txt"), "-o", "x.wav"]))
+
+
+def test_header_is_valid_c99():
+    """include/vfx_b200.h is the C ABI: it must compile as plain C, not only as C++."""
+    import shutil, subprocess
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("gcc not available")
+    r = subprocess.run([gcc, "-std=c99", "-fsyntax-only", "-x", "c", os.path.join(ROOT, "include", "vfx_b200.h")],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+
+
+def test_voicefixer_alias_package_resolves_to_b200_classes():
+    import voicefixer
+    from voicefixer_b200 import api
+    assert voicefixer.VoiceFixer is api.VoiceFixer and voicefixer.Vocoder is api.Vocoder
+    with pytest.raises(AttributeError):
+        voicefixer.NoSuchThing
+
+
+def test_wav_loader_mono_mix_and_resample(tmp_path):
+    """librosa.load(path, sr=44100) semantics used by VoiceFixer._load_wav: mean over channels, resample to 44.1 kHz."""
+    from voicefixer_b200 import wavio
+    sr = 22050
+    t = np.arange(sr // 2) / sr
+    left, right = 0.5 * np.sin(2 * np.pi * 440 * t), 0.25 * np.sin(2 * np.pi * 440 * t)
+    pcm = (np.stack([left, right], 1) * 32767).astype("<i2")
+    with wave.open(str(tmp_path / "st.wav"), "wb") as f:
+        f.setnchannels(2); f.setsampwidth(2); f.setframerate(sr); f.writeframes(pcm.tobytes())
+    y = wavio.load_mono(str(tmp_path / "st.wav"), 44100)
+    assert y.dtype == np.float32 and abs(len(y) - 22050) <= 2
+    t2 = np.arange(len(y)) / 44100.0
+    ref = 0.375 * np.sin(2 * np.pi * 440 * t2)
+    assert np.max(np.abs(y[500:-500] - ref[500:-500])) < 5e-3
+    x2 = wavio.read_wave(str(tmp_path / "st.wav"), 44100)
+    assert x2.shape[1] == 2 and abs(x2.shape[0] - 22050) <= 2
