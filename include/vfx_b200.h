@@ -41,6 +41,10 @@ const char* vfx_last_error(void);
 int vfx_version(void);
 
 /* ---- engine lifetime ------------------------------------------------------------------ */
+/* device >= 0: an engine on that sm_100a device.  device == -1: a planning-only engine that makes no
+ * CUDA call -- vfx_engine_set_tensor / vfx_engine_finalize validate a weight set (names and byte sizes)
+ * and vfx_workspace_bytes* size the workspace on a host without a GPU; every launching entry point
+ * refuses it with VFX_ERR_INVALID. */
 int vfx_engine_create(vfx_engine** out, int device, int precision);
 int vfx_engine_destroy(vfx_engine* e);
 
@@ -56,7 +60,11 @@ unsigned long long vfx_launch_count(void);
 /* With option "profile" = 1 every launch group is bracketed by CUDA events on the call's stream;
  * this synchronises, writes one line per tag "tag count total_ms flops bytes" and clears the log. */
 int vfx_profile_report(vfx_engine* e, char* buf, size_t cap);
-/* Resolve every name the engine needs; returns VFX_ERR_MISSING_WEIGHT and lists them otherwise. */
+/* Resolve every name the engine needs; returns VFX_ERR_MISSING_WEIGHT and lists them otherwise.
+ * Two weight sets are complete: analysis + vocoder (VoiceFixer, voicefixer/base.py:11-30), or the
+ * vocoder alone -- nothing but "voc." tensors registered, all present (the reference's stand-alone
+ * Vocoder class, voicefixer/vocoder/base.py:10-40).  On a vocoder-only engine vfx_frontend_mel,
+ * vfx_analysis and vfx_restore return VFX_ERR_INVALID and vfx_workspace_bytes returns 0. */
 int vfx_engine_finalize(vfx_engine* e);
 
 /* Bytes of workspace needed by vfx_restore()/vfx_analysis()/vfx_vocoder() for a batch of B

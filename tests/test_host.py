@@ -114,8 +114,9 @@ def test_wav_io_roundtrip_and_int16_truncation(tmp_path):
     assert pcm.tolist() == [0, 16384, -16384, 32767, -32768, 1, -1]      # astype(np.short): toward zero
     y = wavio.load_mono(str(p), 44100)
     assert y.dtype == np.float32 and y.shape == (7,) and abs(y[1] - 0.5) < 1e-4
-    with pytest.raises(RuntimeError, match="FLAC"):
-        wavio.load_mono("x.flac")
+    with pytest.raises(RuntimeError, match="not a readable FLAC stream"):
+        (tmp_path / "x.flac").write_bytes(b"RIFF....WAVEfmt " + bytes(64))
+        wavio.load_mono(str(tmp_path / "x.flac"))
 
 
 def test_segmentation_matches_reference_loop():
@@ -159,7 +160,9 @@ def test_cli_job_planning_matches_reference_naming(tmp_path):
     with pytest.raises(AssertionError, match="not found"):
         plan_jobs(build_parser().parse_args(["-i", str(tmp_path / "nope.wav")]))
     with pytest.raises(AssertionError, match="Unsupported output format"):
-        plan_jobs(build_parser().parse_args(["-i", str(tmp_path / "in" / "a.wav"), "-o", "x.flac"]))
+        plan_jobs(build_parser().parse_args(["-i", str(tmp_path / "in" / "a.wav"), "-o", "x.mp3"]))
+    jobs = plan_jobs(build_parser().parse_args(["-i", str(tmp_path / "in" / "a.wav"), "-o", "x.flac"]))   # soundfile format
+    assert jobs == [(str(tmp_path / "in" / "a.wav"), "x.flac", 0)]
     with pytest.raises(ValueError, match="only support the .wav"):
         plan_jobs(build_parser().parse_args(["-i", str(tmp_path / "in" / "c.txt"), "-o", "x.wav"]))
 
@@ -199,3 +202,45 @@ def test_wav_loader_mono_mix_and_resample(tmp_path):
     assert np.max(np.abs(y[500:-500] - ref[500:-500])) < 5e-3
     x2 = wavio.read_wave(str(tmp_path / "st.wav"), 44100)
     assert x2.shape[1] == 2 and abs(x2.shape[0] - 22050) <= 2
+
+
+@pytest.mark.parametrize("precision", ["bf16", "fp32"])
+def test_planning_only_engine_validates_weight_sets_and_sizes_workspace(states, precision):
+    """vfx_engine_create(device=-1): finalize + workspace planning without a GPU.  The 20 x 30 s bf16 figure is
+    the one the B200 run reported for the same batch (profiles/r01_bench_longform_N1.json: 17.168495616 GB)."""
+    import ctypes
+    from voicefixer_b200 import _lib
+    from voicefixer_b200.engine import Planner
+    from voicefixer_b200.weights import pack_analysis, pack_vocoder
+    voc = pack_vocoder(states[1], precision)
+    full = dict(pack_analysis(states[0], precision), **voc)
+    pl = Planner(full, precision)
+    if precision == "bf16":
+        assert pl.workspace_bytes(20, 44100 * 30) == 17168495616
+    small, big = pl.workspace_bytes(1, 44100), pl.workspace_bytes(8, 441000)
+    assert 0 < small < big and pl.workspace_bytes(8, 441000) == big            # deterministic
+    assert pl.workspace_bytes(1, 1024) == 0 and pl.workspace_bytes(0, 44100) == 0
+    # the reference's stand-alone Vocoder (vocoder/base.py:10-40) loads the synthesis checkpoint only
+    pv = Planner(voc, precision)
+    assert pv.workspace_bytes(1, 44100) == 0                                   # restore() needs the analysis module
+    assert 0 < pv.workspace_bytes_frames(2, 101) <= pl.workspace_bytes_frames(2, 101)
+    # incomplete or inconsistent weight sets are named, not guessed at
+    bad = dict(full); del bad["unet.head.w"]
+    with pytest.raises(_lib.VfxError, match=r"missing weight tensors: unet\.head\.w"):
+        Planner(bad, precision)
+    k = sorted(voc)[5]
+    bad = dict(voc); del bad[k]
+    with pytest.raises(_lib.VfxError, match="missing weight tensors: " + k.replace(".", r"\.")):
+        Planner(bad, precision)
+    bad = dict(voc); bad[k] = voc[k].reshape(-1)[:-1]
+    with pytest.raises(_lib.VfxError, match="engine expects"):
+        Planner(bad, precision)
+    bad = dict(voc); bad["dn.bn0.beta"] = full["dn.bn0.beta"]                  # vocoder + a stray analysis tensor
+    with pytest.raises(_lib.VfxError, match="missing weight tensors: dn"):
+        Planner(bad, precision)
+    # a planning-only engine never launches: every compute entry point refuses before touching CUDA
+    lib, one = _lib.load(), ctypes.c_void_p(4096)
+    rc = lib.vfx_restore(pl.h, one, 1, 44100, 0, None, one, one, 1 << 30, None)
+    assert rc == -1 and b"planning-only" in lib.vfx_last_error()
+    rc = lib.vfx_vocoder(pv.h, one, 1, 8, 0, one, -1, 1.0, one, 1 << 30, None)
+    assert rc == -1 and b"planning-only" in lib.vfx_last_error()

@@ -190,9 +190,20 @@ def test_api_modes_1_2_and_vocoder_oracle(tmp_path, monkeypatch, states):
     with pytest.raises(ValueError, match="more than 1 value per channel"):
         vf.restore_inmem(wav, cuda=True, mode=2)
     wav2 = synthetic.make_utterances(1, seconds=1.6, seed=53)[0]
-    out2 = vf.restore_inmem(wav2, cuda=True, mode=2)
+    out2 = vf.restore_inmem(wav2, cuda=True, mode=2, drop_masks_fn=False)   # train-mode BN only: deterministic
     ref2 = O.restore_inmem(wav2, states[0], states[1], mode=2)
     assert out2.shape == (1, wav2.shape[0]) and rel_rms(out2, ref2) < 5e-4
+    # explicit masks through the API == the oracle with the same masks; the default draws them from torch's RNG
+    T2 = 1 + wav2.shape[0] // 441
+    keep = torch.rand(2, 1, T2, 512, generator=torch.Generator().manual_seed(5)) >= 0.5
+    out2m = vf.restore_inmem(wav2, cuda=True, mode=2, drop_masks_fn=lambda B, T: keep)
+    ref2m = O.restore_inmem(wav2, states[0], states[1], mode=2, drop_masks_fn=lambda T: keep[:, :1])
+    assert rel_rms(out2m, ref2m) < 5e-4 and rel_rms(out2m, out2) > 1e-2
+    torch.manual_seed(11)
+    out2r = vf.restore_inmem(wav2, cuda=True, mode=2)                        # reference default: random dropout
+    assert out2r.shape == out2.shape and np.isfinite(out2r).all() and rel_rms(out2r, out2) > 1e-2
+    with pytest.raises(ValueError, match="dropout masks must have shape"):
+        vf.restore_inmem(wav2, cuda=True, mode=2, drop_masks_fn=lambda B, T: keep[:, :, :-1])
     with pytest.raises(ValueError):
         vf.restore_inmem(wav, cuda=True, mode=3)
     # Vocoder.oracle: wav file -> |STFT| -> Slaney mel -> Generator -> int16 wav file (vocoder/base.py:58-77)

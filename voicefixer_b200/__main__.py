@@ -12,7 +12,7 @@ import re
 import sys
 import time
 
-OUTPUT_FORMATS = {"WAV"}                       # stdlib `wave` writer (soundfile is not in this image)
+OUTPUT_FORMATS = {"WAV", "FLAC"}               # stdlib `wave` + in-tree FLAC codec (soundfile is not in this image)
 
 
 def build_parser():

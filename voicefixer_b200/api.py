@@ -148,7 +148,11 @@ class VoiceFixer:
     def restore_inmem(self, wav_10k, cuda=False, mode=0, your_vocoder_func=None, drop_masks_fn=None):
         """np (L,) float32 -> np (1, L) float32 (base.py:106-139).  The 30 s segments are
         independent, so all full segments run as one batch and the ragged tail as a
-        second one; results are concatenated in order."""
+        second one; results are concatenated in order.
+
+        drop_masks_fn (extension, mode 2 only): None = random Bernoulli(0.5) keep-masks like the reference's
+        train-mode dropout; a callable (B, T) -> uint8 [2, B, T, 512] supplies them explicitly; False = no
+        dropout (deterministic train-mode BN only)."""
         _check_cuda(cuda)
         if mode not in (0, 1, 2):
             raise ValueError("mode must be 0, 1 or 2")
@@ -174,7 +178,17 @@ class VoiceFixer:
             x = torch.from_numpy(np.stack([segs[i] for i in idxs])).to(dev)
             if mode == 1:
                 x, _ = eng.hf_cut(x)                                     # shorter: 512*(L//512)
-            masks = drop_masks_fn(x.shape[0], 1 + x.shape[1] // 441) if (mode == 2 and drop_masks_fn) else None
+            masks = None
+            if mode == 2 and drop_masks_fn is not False:
+                T = 1 + x.shape[1] // 441
+                # the reference's mode 2 is module.train(): both Dropout(0.5) of the denoiser are live and draw
+                # from torch's global RNG (base.py:114-115, restorer/model.py:76,90).  Same distribution here
+                # (keep-masks from torch's CPU generator, so torch.manual_seed controls it); the RNG *stream*
+                # differs from the reference's, which no reference test pins.  drop_masks_fn=False disables it.
+                masks = drop_masks_fn(x.shape[0], T) if drop_masks_fn else (torch.rand(2, x.shape[0], T, 512) >= 0.5)
+                masks = torch.as_tensor(masks).to(torch.uint8)
+                if tuple(masks.shape) != (2, x.shape[0], T, 512):
+                    raise ValueError(f"dropout masks must have shape (2, {x.shape[0]}, {T}, 512), got {tuple(masks.shape)}")
             if your_vocoder_func is None:
                 y = eng.restore(x, mode=2 if mode == 2 else 0, drop_masks=masks)
             else:                                                        # base.py:126-129

@@ -1,4 +1,5 @@
-"""Builds voicefixer_b200/libvfx_b200.so in-tree with nvcc for sm_100a (no JIT cache)."""
+"""Builds voicefixer_b200/libvfx_b200.so in-tree with nvcc for sm_100a (no JIT cache), and the
+host-only audio file codec voicefixer_b200/libvfx_hostio.so with gcc."""
 import os
 import subprocess
 import sys
@@ -10,6 +11,23 @@ SOURCES = ["engine.cu", "conv_gemm_simt.cu", "conv_gemm_tc.cu", "elementwise.cu"
            "gru.cu", "hf_cut.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
+
+
+HOSTIO_SRC = os.path.join(HERE, "hostio", "flac_codec.c")
+HOSTIO_LIB = os.path.join(HERE, "libvfx_hostio.so")
+
+
+def build_hostio(force=False):
+    """gcc -> libvfx_hostio.so (include/vfx_hostio.h: FLAC reader / writer for the file API)."""
+    hdr = os.path.join(HERE, "..", "include", "vfx_hostio.h")
+    if (not force and os.path.exists(HOSTIO_LIB) and os.path.getmtime(HOSTIO_LIB) >= os.path.getmtime(HOSTIO_SRC)
+            and os.path.getmtime(HOSTIO_LIB) >= os.path.getmtime(hdr)):
+        return HOSTIO_LIB
+    cmd = [os.environ.get("CC", "gcc"), "-O2", "-std=c11", "-Wall", "-Wextra", "-fPIC", "-shared", "-o", HOSTIO_LIB, HOSTIO_SRC]
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("gcc failed on flac_codec.c:\n" + r.stdout)
+    return HOSTIO_LIB
 
 
 def _nvcc():
@@ -29,6 +47,7 @@ def needs_build():
 
 
 def build(force=False, verbose=False):
+    build_hostio(force)
     if not force and not needs_build():
         return LIB
     objdir = os.path.join(HERE, "build")

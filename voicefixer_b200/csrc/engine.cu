@@ -29,8 +29,10 @@ struct ProfRec { std::string tag; cudaEvent_t a, b; double flops, bytes; };
 
 }  // namespace vfx
 
+enum { VFX_PART_ANALYSIS = 1, VFX_PART_VOCODER = 2 };   // analysis = front end + denoiser + UNet ("fe.", "dn.", "unet.")
+
 struct vfx_engine {
-  int device = 0;
+  int device = 0;   // -1: planning-only engine (no CUDA calls; finalize and workspace queries only)
   int precision = VFX_PREC_FP32;
   bool finalized = false;
   int use_tc = 1;   // BF16: tcgen05 kernel where the shape allows (0 = SIMT bf16 cross-check)
@@ -38,6 +40,7 @@ struct vfx_engine {
   float* d_window = nullptr;    // periodic Hann, 2048
   float2* d_tw = nullptr;       // exp(-2 pi i k / 2048), k < 1024
   std::vector<std::string> missing;
+  int parts = 0;    // VFX_PART_* bits of the weight sets found complete by vfx_engine_finalize
   int profile = 0;
   std::vector<vfx::ProfRec> prof;
   std::string prof_report;
@@ -655,6 +658,12 @@ int vfx_version(void) { return 100; }
 int vfx_engine_create(vfx_engine** out, int device, int precision) {
   VFX_REQUIRE(out != nullptr, "engine_create: out is null");
   VFX_REQUIRE(precision == VFX_PREC_FP32 || precision == VFX_PREC_BF16, "engine_create: bad precision %d", precision);
+  if (device == -1) {   // planning-only: weight-set validation and workspace sizing on a host without a GPU
+    vfx_engine* e = new vfx_engine();
+    e->device = -1; e->precision = precision;
+    *out = e;
+    return VFX_OK;
+  }
   int ndev = 0;
   VFX_CUDA_CHECK(cudaGetDeviceCount(&ndev));
   VFX_REQUIRE(device >= 0 && device < ndev, "engine_create: device %d not present (%d devices)", device, ndev);
@@ -684,8 +693,10 @@ int vfx_engine_create(vfx_engine** out, int device, int precision) {
 
 int vfx_engine_destroy(vfx_engine* e) {
   if (!e) return VFX_OK;
-  cudaFree(e->d_window);
-  cudaFree(e->d_tw);
+  if (e->device >= 0) {
+    cudaFree(e->d_window);
+    cudaFree(e->d_tw);
+  }
   delete e;
   return VFX_OK;
 }
@@ -694,6 +705,7 @@ unsigned long long vfx_launch_count(void) { return vfx::g_launches; }
 
 int vfx_profile_report(vfx_engine* e, char* buf, size_t cap) {
   VFX_REQUIRE(e && buf && cap > 0, "profile_report: bad arguments");
+  VFX_REQUIRE(e->device >= 0, "profile_report: planning-only engine");
   VFX_CUDA_CHECK(cudaSetDevice(e->device));
   VFX_CUDA_CHECK(cudaDeviceSynchronize());
   struct Agg { double ms = 0, flops = 0, bytes = 0; long n = 0; };
@@ -741,7 +753,8 @@ static int dry_run(vfx_engine* e, int B, int T, int L, size_t* bytes) {
   if (L > 0) r = restore_forward(c, nullptr, B, L, nullptr, nullptr);
   else {
     float* mel = ws.alloc<float>((size_t)B * T * 128);
-    r = analysis_forward(c, mel, B, T, nullptr, mel);
+    const bool voc_only = e->finalized && !(e->parts & VFX_PART_ANALYSIS);
+    r = voc_only ? VFX_OK : analysis_forward(c, mel, B, T, nullptr, mel);
     if (r == VFX_OK) r = vocoder_forward(c, mel, B, T, 1, nullptr, -1, 1.f);
   }
   *bytes = ws.peak + 4096;
@@ -760,6 +773,25 @@ int vfx_engine_finalize(vfx_engine* e) {
     if (r == VFX_OK) r = r2;
   }
   if (!e->missing.empty()) {
+    // The reference's stand-alone Vocoder class (voicefixer/vocoder/base.py:10-40) loads the synthesis checkpoint only.
+    // An engine that holds nothing but "voc." tensors, all of them present, is complete for vfx_vocoder /
+    // vfx_vocoder_cond; the analysis-side entry points refuse it.
+    bool voc_only = !e->tensors.empty();
+    for (auto& kv : e->tensors) if (kv.first.rfind("voc.", 0) != 0) voc_only = false;
+    if (voc_only) {
+      std::vector<std::string> analysis_missing;
+      analysis_missing.swap(e->missing);
+      Bump ws(nullptr, 0);
+      Ctx c{e, nullptr, &ws, true, VFX_MODE_EVAL};
+      float* mel = ws.alloc<float>((size_t)64 * 128);
+      const int rv = vocoder_forward(c, mel, 1, 64, 1, nullptr, -1, 1.f);
+      if (rv == VFX_OK && c.rc == VFX_OK && e->missing.empty()) {
+        e->parts = VFX_PART_VOCODER;
+        e->finalized = true;
+        return VFX_OK;
+      }
+      if (e->missing.empty()) return rv != VFX_OK ? rv : c.rc;     // e.g. a tensor of the wrong size: message already set
+    }
     std::string s = "missing weight tensors:";
     for (size_t i = 0; i < e->missing.size() && i < 12; ++i) s += " " + e->missing[i];
     if (e->missing.size() > 12) s += " ...";
@@ -767,12 +799,14 @@ int vfx_engine_finalize(vfx_engine* e) {
     return VFX_ERR_MISSING_WEIGHT;
   }
   if (r != VFX_OK) return r;
+  e->parts = VFX_PART_ANALYSIS | VFX_PART_VOCODER;
   e->finalized = true;
   return VFX_OK;
 }
 
 size_t vfx_workspace_bytes(const vfx_engine* e, int B, int L) {
   if (!e || B <= 0 || L <= 1024) return 0;
+  if (e->finalized && !(e->parts & VFX_PART_ANALYSIS)) return 0;   // restore() needs the analysis weights
   size_t bytes = 0;
   dry_run(const_cast<vfx_engine*>(e), B, 0, L, &bytes);
   return bytes;
@@ -788,7 +822,12 @@ size_t vfx_workspace_bytes_frames(const vfx_engine* e, int B, int T) {
 #define VFX_ENTER(e)                                                                     \
   VFX_REQUIRE((e) != nullptr, "null engine");                                            \
   VFX_REQUIRE((e)->finalized, "engine not finalized (call vfx_engine_finalize)");        \
+  VFX_REQUIRE((e)->device >= 0, "planning-only engine (device -1) cannot launch work");  \
   VFX_CUDA_CHECK(cudaSetDevice((e)->device))
+
+#define VFX_NEED_ANALYSIS(e)                                                              \
+  VFX_REQUIRE((e)->parts & VFX_PART_ANALYSIS,                                            \
+              "this engine holds the vocoder weights only (stand-alone Vocoder); the analysis module is not loaded")
 
 #define VFX_FINISH(c, ws)                                                                \
   if ((ws).overflow) { set_error("workspace too small: need %zu bytes", (ws).peak); return VFX_ERR_WORKSPACE; } \
@@ -796,6 +835,7 @@ size_t vfx_workspace_bytes_frames(const vfx_engine* e, int B, int T) {
 
 int vfx_frontend_mel(vfx_engine* e, const float* wav, int B, int L, float* mel, float* sp_out, void* stream) {
   VFX_ENTER(e);
+  VFX_NEED_ANALYSIS(e);
   VFX_REQUIRE(wav && mel && B > 0, "frontend: bad arguments");
   Bump ws(nullptr, 0);
   Ctx c{e, (cudaStream_t)stream, &ws, false, VFX_MODE_EVAL};
@@ -805,6 +845,7 @@ int vfx_frontend_mel(vfx_engine* e, const float* wav, int B, int L, float* mel, 
 int vfx_analysis(vfx_engine* e, const float* mel, int B, int T, int mode, const uint8_t* drop_masks,
                  float* mel_log_out, void* workspace, size_t workspace_bytes, void* stream) {
   VFX_ENTER(e);
+  VFX_NEED_ANALYSIS(e);
   VFX_REQUIRE(mel && mel_log_out && B > 0 && T > 0 && workspace, "analysis: bad arguments");
   VFX_REQUIRE(mode == VFX_MODE_EVAL || mode == VFX_MODE_TRAIN_BN, "analysis: bad mode %d", mode);
   Bump ws(workspace, workspace_bytes);
@@ -843,6 +884,7 @@ int vfx_vocoder_cond(vfx_engine* e, const float* cond, int B, int Tc, float* wav
 int vfx_restore(vfx_engine* e, const float* wav, int B, int L, int mode, const uint8_t* drop_masks,
                 float* wav_out, void* workspace, size_t workspace_bytes, void* stream) {
   VFX_ENTER(e);
+  VFX_NEED_ANALYSIS(e);
   VFX_REQUIRE(wav && wav_out && B > 0 && workspace, "restore: bad arguments");
   VFX_REQUIRE(mode == VFX_MODE_EVAL || mode == VFX_MODE_TRAIN_BN, "restore: bad mode %d", mode);
   VFX_REQUIRE(L > 1024, "restore: L=%d must exceed 1024 samples", L);

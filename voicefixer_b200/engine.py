@@ -25,6 +25,37 @@ def default_precision():
     return os.environ.get("VFX_PRECISION", "fp32")
 
 
+class Planner:
+    """Planning-only engine (vfx_engine_create with device -1): validates a packed weight set against what the
+    kernels expect (names, byte sizes) and sizes the activation workspace for a batch -- no GPU, no CUDA call.
+    `packed`: {name: CPU tensor} from weights.pack_analysis / pack_vocoder (either both, or the vocoder alone)."""
+
+    def __init__(self, packed, precision):
+        self.lib = _lib.load()
+        self.precision = precision
+        h = ctypes.c_void_p()
+        _lib.check(self.lib.vfx_engine_create(ctypes.byref(h), -1, _lib.PREC[precision]), "vfx_engine_create")
+        self.h = h
+        table, self.weight_bytes = Engine.layout(packed)
+        for name, off, nbytes in table:          # addresses are never dereferenced by a planning-only engine
+            _lib.check(self.lib.vfx_engine_set_tensor(self.h, name.encode(), ctypes.c_void_p(ALIGN + off), nbytes),
+                       f"set_tensor({name})")
+        _lib.check(self.lib.vfx_engine_finalize(self.h), "vfx_engine_finalize")
+
+    def workspace_bytes(self, B, L):
+        """restore() on B items of L samples; 0 for a vocoder-only weight set."""
+        return int(self.lib.vfx_workspace_bytes(self.h, int(B), int(L)))
+
+    def workspace_bytes_frames(self, B, T):
+        """analysis / vocoder entry points on B items of T mel frames."""
+        return int(self.lib.vfx_workspace_bytes_frames(self.h, int(B), int(T)))
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.lib.vfx_engine_destroy(self.h)
+            self.h = None
+
+
 class Engine:
     """One engine per process / GPU.  `ana`, `voc`: reference-layout state dicts (CPU tensors)."""
 

@@ -1,4 +1,7 @@
-"""Host WAV I/O for the public API (stdlib `wave`; librosa/soundfile are not in this image).
+"""Host audio file I/O for the public API (librosa / soundfile are not in this image): WAV through
+stdlib `wave`, FLAC through the in-tree C codec (include/vfx_hostio.h) -- the container follows the
+file extension, as librosa.load / soundfile.write do for the reference (its test/test.py:48-57 is
+FLAC in, FLAC out).
 
 Mirrors voicefixer/tools/wav.py:9-37 (save_wave: x 2^15, int16 truncation) and :116-149
 (read_wave) / librosa.load(sr=44100) mono mix used by VoiceFixer._load_wav (base.py:47-49)."""
@@ -8,7 +11,10 @@ import numpy as np
 
 def _read_pcm(path):
     if str(path).lower().endswith(".flac"):
-        raise RuntimeError("FLAC decoding is not available in this build (no soundfile/librosa); use WAV")
+        from . import _hostio
+        with open(str(path), "rb") as f:
+            pcm, sr, bps = _hostio.flac_decode(f.read())
+        return pcm.astype(np.float32) / np.float32(1 << (bps - 1)), sr
     with wave.open(str(path), "rb") as f:
         nch, sw, sr, nfr = f.getnchannels(), f.getsampwidth(), f.getframerate(), f.getnframes()
         raw = f.readframes(nfr)
@@ -70,6 +76,11 @@ def save_wave(frames, fname, sample_rate=44100):
         frames = frames[0, ...]
     if frames.ndim == 1:
         frames = frames[:, None]
+    if str(fname).lower().endswith(".flac"):         # soundfile.write picks the container from the extension
+        from . import _hostio
+        with open(str(fname), "wb") as f:
+            f.write(_hostio.flac_encode_int16(frames, sample_rate))
+        return
     with wave.open(str(fname), "wb") as f:
         f.setnchannels(frames.shape[1])
         f.setsampwidth(2)
