@@ -160,3 +160,128 @@ def test_decode_every_reference_flac_against_its_libflac_md5():
         ref = np.frombuffer(w.readframes(w.getnframes()), dtype="<i2")
     got = wavio.load_mono(os.path.join(REF_UTT, "original", "original.flac"))
     assert np.array_equal(got, ref.astype(np.float32) / 32768.0)
+
+
+# ------------------------------------------------------------------ decoder paths no available file reaches
+def _decode(data):
+    from voicefixer_b200 import _hostio
+    pcm, sr, bps = _hostio.flac_decode(data)
+    return pcm, sr, bps
+
+
+def test_decode_stereo_decorrelation_modes():
+    """left/side (8), side/right (9), mid/side (10): the side channel carries bps + 1 bits."""
+    import flac_writer as W
+    rng = np.random.default_rng(1)
+    n = 192
+    left = rng.integers(-32768, 32768, n).tolist()
+    right = rng.integers(-32768, 32768, n).tolist()
+    left[0], right[0], left[1], right[1] = 32767, -32768, -32768, 32767            # extreme side values
+    side = [l - r for l, r in zip(left, right)]
+    mid = [(l + r) >> 1 for l, r in zip(left, right)]
+    inter = [v for lr in zip(left, right) for v in lr]
+    plans = {8: (left, 16, side, 17), 9: (side, 17, right, 16), 10: (mid, 16, side, 17), 1: (left, 16, right, 16)}
+    for ch_code, (c0, b0, c1, b1) in plans.items():
+        fr = W.frame(0, n, ch_code, 16, [lambda b, c0=c0, b0=b0: W.sub_verbatim(b, c0, b0),
+                                         lambda b, c1=c1, b1=b1: W.sub_verbatim(b, c1, b1)])
+        pcm, sr, bps = _decode(W.stream([fr], 44100, 2, 16, n, inter))
+        assert np.array_equal(pcm[:, 0], left) and np.array_equal(pcm[:, 1], right), ch_code
+
+
+@pytest.mark.parametrize("bps", [8, 12, 20, 24])
+def test_decode_other_bit_depths_and_scaling(bps, tmp_path):
+    import flac_writer as W
+    from voicefixer_b200 import wavio
+    rng = np.random.default_rng(bps)
+    lo, hi = -(1 << (bps - 1)), (1 << (bps - 1))
+    x = rng.integers(lo, hi, 256).tolist()
+    x[0], x[1] = lo, hi - 1
+    fr = W.frame(0, 256, 0, bps, [lambda b: W.sub_verbatim(b, x, bps)], ss_from_info=(bps == 12))
+    data = W.stream([fr], 48000, 1, bps, 256, x)
+    pcm, sr, got_bps = _decode(data)
+    assert (sr, got_bps) == (48000, bps) and np.array_equal(pcm[:, 0], x)
+    (tmp_path / "d.flac").write_bytes(data)
+    y = wavio.read_wave(str(tmp_path / "d.flac"), 48000)                           # float32 in [-1, 1)
+    assert y.shape == (256, 1) and y[0, 0] == -1.0 and abs(y[1, 0] - (hi - 1) / hi) < 1e-7
+
+
+def test_decode_subframe_types_partitions_and_escape_codes():
+    """CONSTANT, wasted bits, FIXED 0-4 with partitioned Rice (4- and 5-bit parameters) and escape partitions
+    (raw n-bit residuals, n = 0 included), LPC with explicit precision / shift."""
+    import flac_writer as W
+    rng = np.random.default_rng(7)
+    n = 256
+    t = np.arange(n)
+    smooth = (9000 * np.sin(2 * np.pi * t / 57.0) + 30 * rng.standard_normal(n)).astype(int).tolist()
+    cases = []
+    cases.append(("constant", lambda b: W.sub_constant(b, [-1234] * n, 16), [-1234] * n))
+    w = (rng.integers(-2000, 2000, n) * 8).tolist()
+    cases.append(("wasted3", lambda b: W.sub_verbatim(b, w, 16, wasted=3), w))
+    for order in range(5):
+        cases.append((f"fixed{order}", lambda b, o=order: W.sub_fixed(b, smooth, 16, o, 2, [9, 8, 10, 9]), smooth))
+    cases.append(("rice2", lambda b: W.sub_fixed(b, smooth, 16, 1, 1, [17, 3], method=1), smooth))
+    cases.append(("escape", lambda b: W.sub_fixed(b, smooth, 16, 2, 2, [8, ("esc", 14), 9, ("esc", 13)]), smooth))
+    ramp = [3 * i - 100 for i in range(n)]                                         # order-2 residual is all zero
+    cases.append(("escape0", lambda b: W.sub_fixed(b, ramp, 16, 2, 1, [("esc", 0), ("esc", 0)]), ramp))
+    cases.append(("lpc", lambda b: W.sub_lpc(b, smooth, 16, [117, -60, 5], 8, 6, 3, [7] * 8), smooth))
+    cases.append(("lpc32", lambda b: W.sub_lpc(b, smooth, 16, [1] * 32, 3, 5, 0, [15], method=1), smooth))
+    for name, sub, expect in cases:
+        pcm, _, _ = _decode(W.stream([W.frame(0, n, 0, 16, [sub])], 44100, 1, 16, n, expect))
+        assert np.array_equal(pcm[:, 0], expect), name
+
+
+def test_decode_frame_header_variants():
+    """Blocksize codes (table, 8-bit, 16-bit), sample-rate codes (table, kHz byte, Hz, tens of Hz), fixed and variable
+    blocking with multi-byte frame / sample numbers, unknown total_samples, unset MD5, trailing bytes after the audio."""
+    import flac_writer as W
+    rng = np.random.default_rng(11)
+
+    def verb(x):
+        return [lambda b: W.sub_verbatim(b, x, 16)]
+
+    blocks = [(192, {}), (576, {}), (256, {}), (100, dict(bs_explicit=8)), (1000, dict(bs_explicit=16)), (17, dict(bs_explicit=8))]
+    xs = [rng.integers(-500, 500, n).tolist() for n, _ in blocks]
+    total = sum(n for n, _ in blocks)
+    flat = [v for x in xs for v in x]
+    # variable blocking: the header number is the first sample of the frame (here offset so it needs 2-5 bytes)
+    frames, pos = [], 0
+    for (n, kw), x in zip(blocks, xs):
+        frames.append(W.frame(pos, n, 0, 16, verb(x), variable=True, sr_code=9, **kw))
+        pos += n
+    pcm, sr, _ = _decode(W.stream(frames, 44100, 1, 16, total, flat))
+    assert sr == 44100 and np.array_equal(pcm[:, 0], flat)
+    for number in (0x7F, 0x80, 0x7FF, 0x800, 0xFFFF, 0x10000, 0x1FFFFF, 0x200000, 0x3FFFFFF, 0x4000000, 0x7FFFFFFF):
+        fr = W.frame(number, 192, 0, 16, verb(xs[0]))
+        assert np.array_equal(_decode(W.stream([fr], 44100, 1, 16, 192, xs[0]))[0][:, 0], xs[0]), hex(number)
+    big = W.frame((1 << 35) + 5, 192, 0, 16, verb(xs[0]), variable=True)            # 36-bit sample number, 7 bytes
+    assert np.array_equal(_decode(W.stream([big], 44100, 1, 16, 192, xs[0]))[0][:, 0], xs[0])
+    for sr, code, extra in ((32000, 12, bytes([32])), (12345, 13, (12345).to_bytes(2, "big")), (22050, 14, (2205).to_bytes(2, "big")),
+                            (96000, 11, b""), (8000, 4, b"")):
+        fr = W.frame(0, 192, 0, 16, verb(xs[0]), sr_code=code, sr_extra=extra)
+        pcm, got_sr, _ = _decode(W.stream([fr], sr, 1, 16, 192, xs[0]))
+        assert got_sr == sr and np.array_equal(pcm[:, 0], xs[0])
+    # unknown length + no signature + junk after the last frame (e.g. an ID3v1 tag)
+    frames = [W.frame(i, 192, 0, 16, verb(xs[0])) for i in range(3)]
+    pcm, _, _ = _decode(W.stream(frames, 44100, 1, 16, 0, None) + b"TAG" + bytes(125))
+    assert pcm.shape == (576, 1) and np.array_equal(pcm[:192, 0], xs[0]) and np.array_equal(pcm[384:, 0], xs[0])
+
+
+def test_decode_rejects_reserved_fields():
+    import flac_writer as W
+    from voicefixer_b200 import _hostio
+    x = list(range(192))
+
+    def one(mutate):
+        b = W.Bits()
+        mutate(b)
+        return b
+
+    bad_type = lambda b: (b.put(0, 1), b.put(2, 6), b.put(0, 1), [b.signed(v, 16) for v in x])          # reserved subframe type
+    with pytest.raises(RuntimeError, match="reserved subframe type"):
+        _hostio.flac_decode(W.stream([W.frame(0, 192, 0, 16, [bad_type])], 44100, 1, 16, 192, x))
+    bad_method = lambda b: (b.put(0, 1), b.put(8, 6), b.put(0, 1), b.put(2, 2), b.put(0, 4))            # residual method 2
+    with pytest.raises(RuntimeError, match="reserved residual coding method"):
+        _hostio.flac_decode(W.stream([W.frame(0, 192, 0, 16, [bad_method])], 44100, 1, 16, 192, x))
+    with pytest.raises(RuntimeError, match="channel"):                                                      # 2 channels in a mono stream
+        fr = W.frame(0, 192, 1, 16, [lambda b: W.sub_verbatim(b, x, 16)] * 2)
+        _hostio.flac_decode(W.stream([fr], 44100, 1, 16, 192, x))
