@@ -244,3 +244,91 @@ def test_planning_only_engine_validates_weight_sets_and_sizes_workspace(states, 
     assert rc == -1 and b"planning-only" in lib.vfx_last_error()
     rc = lib.vfx_vocoder(pv.h, one, 1, 8, 0, one, -1, 1.0, one, 1 << 30, None)
     assert rc == -1 and b"planning-only" in lib.vfx_last_error()
+
+
+def test_cli_pipeline_overlaps_io_keeps_order_and_propagates_errors():
+    """run_jobs: reader thread -> GPU stage -> writer thread (disk -> GPU -> disk must keep up)."""
+    import threading, time as _t
+    from voicefixer_b200.__main__ import run_jobs
+    jobs = [(f"in{i}.wav", f"out{i}.wav", 0) for i in range(6)] + [("in5.wav", "out5-mode1.wav", 1)]
+    log, lock = [], threading.Lock()
+
+    def rec(*a):
+        with lock:
+            log.append(a)
+
+    def load(src):
+        _t.sleep(0.05); rec("load", src); return src + ":pcm"
+
+    def restore(wav, mode):
+        _t.sleep(0.05); rec("gpu", wav, mode); return wav + ":restored%d" % mode
+
+    def save(out, dst):
+        _t.sleep(0.05); rec("save", out, dst)
+
+    t0 = _t.time()
+    took = run_jobs(jobs, load, restore, save, say=lambda *a: None)
+    wall = _t.time() - t0
+    assert len(took) == 7 and wall < 0.85 * (6 + 7 + 7) * 0.05                      # stages overlap (serial = 1.0 s)
+    assert [e[1] for e in log if e[0] == "load"] == [f"in{i}.wav" for i in range(6)]  # in5.wav decoded once for two modes
+    assert [e[2] for e in log if e[0] == "save"] == [j[1] for j in jobs]              # results written in job order
+    assert ("save", "in5.wav:pcm:restored1", "out5-mode1.wav") in log
+
+    def bad_load(src):
+        if src == "in2.wav":
+            raise FileNotFoundError(src)
+        return load(src)
+
+    log.clear()
+    with pytest.raises(FileNotFoundError, match="in2.wav"):
+        run_jobs(jobs, bad_load, restore, save, say=lambda *a: None)
+    assert [e[2] for e in log if e[0] == "save"] == ["out0.wav", "out1.wav"]          # finished work is kept, nothing after
+
+    def bad_gpu(wav, mode):
+        if wav.startswith("in3"):
+            raise RuntimeError("device fault")
+        return restore(wav, mode)
+
+    log.clear()
+    with pytest.raises(RuntimeError, match="device fault"):
+        run_jobs(jobs, load, bad_gpu, save, say=lambda *a: None)
+    assert "out3.wav" not in [e[2] for e in log if e[0] == "save"]
+
+    def bad_save(out, dst):
+        if dst == "out1.wav":
+            raise OSError("disk full")
+        save(out, dst)
+
+    with pytest.raises(OSError, match="disk full"):
+        run_jobs(jobs, load, restore, bad_save, say=lambda *a: None)
+    assert threading.active_count() < 10                                             # no leaked pipeline threads
+    assert run_jobs([], load, restore, save) == []
+
+
+def test_cli_main_wiring_folder_mode_all_with_flac_output(tmp_path, monkeypatch, capsys):
+    """`python -m voicefixer_b200` end to end on the host side (decode -> [GPU stage stubbed] -> encode): file naming of
+    --mode all, FLAC / WAV by extension, messages.  The GPU stage itself is covered by the -m gpu tests."""
+    from voicefixer_b200 import api, wavio, __main__ as cli
+
+    class StubFixer:
+        def _load_wav(self, path, sample_rate):
+            return wavio.load_mono(path, sample_rate)
+
+        def restore_inmem(self, wav, cuda=False, mode=0):
+            return (wav[: 512 * (len(wav) // 512)] if mode == 1 else wav)[None] * 0.5      # (1, N) float32
+
+    monkeypatch.setattr(api, "VoiceFixer", StubFixer)
+    rng = np.random.default_rng(0)
+    os.makedirs(tmp_path / "in")
+    for name, n in (("a.wav", 5000), ("b.wav", 7000)):
+        wavio.save_wave((0.5 * rng.standard_normal((1, n))).clip(-1, 1).astype(np.float32), str(tmp_path / "in" / name))
+    assert cli.main(["--infolder", str(tmp_path / "in"), "--outfolder", str(tmp_path / "out"), "--mode", "all"]) == 0
+    assert sorted(os.listdir(tmp_path / "out")) == [f"{s}-mode{m}.wav" for s in "ab" for m in (0, 1, 2)]
+    a = wavio.load_mono(str(tmp_path / "in" / "a.wav"))
+    assert np.allclose(wavio.load_mono(str(tmp_path / "out" / "a-mode0.wav")), a * 0.5, atol=1 / 32768)
+    assert wavio.load_mono(str(tmp_path / "out" / "a-mode1.wav")).shape == (512 * (5000 // 512),)
+    out = capsys.readouterr().out
+    assert out.count("Restoration took") == 6 and "Initializing VoiceFixer" in out and "mode=2" in out
+    assert cli.main(["-i", str(tmp_path / "in" / "b.wav"), "-o", str(tmp_path / "x" / "b.flac"), "--silent"]) == 0
+    assert (tmp_path / "x" / "b.flac").read_bytes()[:4] == b"fLaC"
+    assert wavio.load_mono(str(tmp_path / "x" / "b.flac")).shape == (7000,)

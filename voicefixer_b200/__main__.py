@@ -5,7 +5,7 @@
 
 Same flags, same output naming (`--mode all` writes `<name>-mode<k><ext>` for k = 0,1,2), same
 `.wav`-only input rule, same messages.  The work is planned first (`plan_jobs`, a pure function) and
-then executed with one VoiceFixer instance."""
+then executed with one VoiceFixer instance as a reader -> GPU -> writer pipeline (`run_jobs`)."""
 import argparse
 import os
 import re
@@ -69,6 +69,85 @@ def plan_jobs(args):
     return jobs
 
 
+def run_jobs(jobs, load, restore, save, say=print, depth=2):
+    """Executes [(src, dst, mode)] as a three-stage pipeline so that disk and codec time hide behind GPU time:
+    a reader thread decodes / resamples the next inputs (`load(src)`), the calling thread runs `restore(wav, mode)`
+    on the GPU, a writer thread encodes and writes the previous results (`save(out, dst)`).  At most `depth` decoded
+    inputs and `depth` finished outputs are in flight.  Jobs complete in order; like the sequential loop of the reference,
+    every job before a failing one is still written, nothing after it is started, and the exception is re-raised once
+    the threads have drained.  A source that is
+    used by consecutive jobs (`--mode all`) is decoded once.  Returns the per-job GPU-stage seconds."""
+    import queue
+    import threading
+    loaded, finished, took = queue.Queue(maxsize=depth), queue.Queue(maxsize=depth), []
+    stop, write_errors = threading.Event(), []
+
+    def reader():                                        # failures travel down the queue IN ORDER, so that every
+        last_src, last_wav = None, None                  # job before the failing one still completes
+        try:
+            for job in jobs:
+                if stop.is_set():
+                    break
+                if job[0] != last_src:
+                    last_src, last_wav = job[0], load(job[0])
+                loaded.put((job, last_wav))
+        except BaseException as e:                       # noqa: BLE001 - re-raised by the caller's thread
+            loaded.put(e)
+        finally:
+            loaded.put(None)
+
+    def writer():
+        while True:
+            item = finished.get()
+            if item is None:
+                return
+            if write_errors:
+                continue                                 # drain
+            try:
+                save(item[1], item[0][1])
+            except BaseException as e:                   # noqa: BLE001
+                write_errors.append(e)
+                stop.set()
+
+    threads = [threading.Thread(target=reader, name="vfx-reader", daemon=True),
+               threading.Thread(target=writer, name="vfx-writer", daemon=True)]
+    for t in threads:
+        t.start()
+    failure = None
+    try:
+        while True:
+            item = loaded.get()
+            if item is None:
+                break
+            if failure is not None or stop.is_set():
+                continue                                 # keep draining so the reader can finish
+            if isinstance(item, BaseException):
+                failure = item
+                stop.set()
+                continue
+            (src, dst, mode), wav = item
+            say("Processing {}, mode={}".format(src, mode))
+            t0 = time.time()
+            try:
+                out = restore(wav, mode)
+            except BaseException as e:                   # noqa: BLE001
+                failure = e
+                stop.set()
+                continue
+            took.append(time.time() - t0)
+            print("Restoration took {} s".format(round(took[-1], 1)))
+            finished.put((item[0], out))
+    finally:
+        finished.put(None)
+        for t in threads:
+            t.join()
+    if write_errors:
+        raise write_errors[0]
+    if failure is not None:
+        raise failure
+    return took
+
+
 def main(argv=None):
     args = build_parser().parse_args(argv)
     if args.weight_prepare:
@@ -88,12 +167,13 @@ def main(argv=None):
     from .api import VoiceFixer
     vf = VoiceFixer()
     say("Start processing %d job(s)." % len(jobs))
-    for src, dst, mode in jobs:
-        say("Processing {}, mode={}".format(src, mode))
-        t0 = time.time()
-        vf.restore(input=src, output=dst, cuda=not args.disable_cuda, mode=mode)
-        print("Restoration took {} s".format(round(time.time() - t0, 1)))
-    say("Done")
+    from . import wavio
+    t0 = time.time()
+    run_jobs(jobs,                                                            # = vf.restore(input, output, ...) per job
+             load=lambda src: vf._load_wav(src, sample_rate=44100),          # base.py:141-146, staged
+             restore=lambda wav, mode: vf.restore_inmem(wav, cuda=not args.disable_cuda, mode=mode),
+             save=lambda out, dst: wavio.save_wave(out, fname=dst, sample_rate=44100), say=say)
+    say("Done: {} job(s) in {} s".format(len(jobs), round(time.time() - t0, 1)))
     return 0
 
 
