@@ -8,7 +8,9 @@ One step = one pass of the restore() hot path (vfx_restore: STFT+mel -> denoiser
 trim) over a batch of synthetic degraded utterances (configs[2]: 32 x 10 s per GPU, mode 0; weak
 scaling: every rank processes its own 32).  `value` is device-resident whole-job throughput;
 `e2e` is the same through host buffers (pinned H2D of the inputs + D2H of the waveforms inside
-the timed region).  Prints ONE JSON line on rank 0.
+the timed region).  Prints ONE JSON line on rank 0.  At N=1 the line also carries `cpu_baseline` (the
+oracle port timed on the host cores on a bounded sample) and `parity` (waveform RMS of this engine against
+that oracle output on the same utterance and weights -- the second half of BASELINE.json's metric).
 """
 import argparse
 import json
@@ -131,8 +133,9 @@ def cpu_reference_rate(seconds, threads=None):
 
     def run():
         t0 = time.perf_counter()
-        O.restore_inmem(wav, ana, voc, mode=0)
+        run.out = O.restore_inmem(wav, ana, voc, mode=0)                  # kept: the checker for the parity figure
         return time.perf_counter() - t0
+    run.wav = wav
     return run, threads
 
 
@@ -421,7 +424,7 @@ def main():
                 "whole_step": {"tflops": whole_tf, "frac_of_bf16_sustained": whole_tf / peaks["bf16_tflops_sustained"]}}
     breakdown = {t: round(r["ms"], 3) for t, r in sorted(rep.items(), key=lambda kv: -kv[1]["ms"])}
 
-    cpu_baseline = None
+    cpu_baseline, parity = None, None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         run1, threads = cpu_reference_rate(1.0)
         t1 = run1()
@@ -431,6 +434,20 @@ def main():
         cpu_baseline = {"value": sample_s / dt, "unit": UNIT, "cores": threads, "kind": "port",
                         "sample": f"1 x {sample_s:.0f} s utterance, restore_inmem mode 0 (oracle port, PyTorch fp32), "
                                   f"{dt:.1f} s wall, {threads} of {host_threads()} host threads (fastest of a sweep)"}
+        # BASELINE metric, second half: waveform RMS vs the reference on identical input and weights.  The oracle output
+        # of the baseline sample above is the checker; the engine restores the same utterance (untimed, not in `value`).
+        try:
+            y = eng.restore(torch.from_numpy(run.wav)[None].to(dev)).cpu().numpy().astype(np.float64)
+            ref = np.asarray(run.out, dtype=np.float64).reshape(y.shape)
+            err = float(np.sqrt(np.mean((y - ref) ** 2)))
+            parity = {"wav_rms_err": err, "wav_rms_ref": float(np.sqrt(np.mean(ref ** 2))),
+                      "rel_rms": err / float(np.sqrt(np.mean(ref ** 2))), "mean_abs_err": float(np.mean(np.abs(y - ref))),
+                      "tolerance": "bf16: rel_rms < 3e-2 and mean_abs < 5e-3 (tests/test_parity_gpu.py; reference's own bar: "
+                                   "mean_abs < 1e-2, test/test.py:35)" if args.precision == "bf16"
+                                   else "fp32: rel_rms < 2e-4 (tests/test_parity_gpu.py)",
+                      "sample": f"the cpu_baseline utterance ({sample_s:.0f} s), oracle port vs this engine, same synthetic checkpoints"}
+        except Exception as e:                                             # never let the checker break the measurement
+            parity = {"error": f"{type(e).__name__}: {e}"}
 
     if rank == 0:
         print(json.dumps({
@@ -447,7 +464,7 @@ def main():
             "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e, "h2d_bytes_per_step": B * L * 4,
                     "d2h_bytes_per_step": B * L * 4},
             "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline,
-            "breakdown_ms": breakdown,
+            "parity": parity, "breakdown_ms": breakdown,
         }))
     if world > 1:
         dist.barrier()
