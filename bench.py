@@ -205,6 +205,44 @@ def run_longform(args):
                                  "workspace_gb": eng.workspace_bytes(20, seg) / 1e9}}))
 
 
+def run_vocoder(args):
+    """configs[1]: the synthesis-only path -- Vocoder.forward semantics (vocoder/base.py:42-56) on ONE 10 s utterance's
+    linear 128-bin mel [1, 1001, 128] -> waveform [1, 1006 * 441].  Batch 1 is a latency measurement: `value` is
+    device-resident (CUDA events), `e2e` is host mel -> host waveform."""
+    from voicefixer_b200 import synthetic
+    from voicefixer_b200.engine import Engine
+    torch.cuda.set_device(0)
+    eng = Engine(synthetic.make_analysis_state(0), synthetic.make_vocoder_state(1), device=0, precision=args.precision)
+    wav = torch.from_numpy(synthetic.make_utterances(1, seconds=10.0, seed=1234)).cuda()
+    mel = eng.frontend(wav)                                           # (1, 1001, 128) linear mel of a synthetic utterance
+    host_mel = mel.cpu().pin_memory()
+    T = mel.shape[1]
+    host_out = torch.empty(1, (T + T % 2 + 4) * 441).pin_memory()
+    warm, steps = max(args.warmup, 3), max(args.steps, 10)
+    for _ in range(warm):
+        eng.vocoder(mel)
+    torch.cuda.synchronize()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
+    ev[0].record()
+    for i in range(steps):
+        eng.vocoder(mel)
+        ev[i + 1].record()
+    torch.cuda.synchronize()
+    ms = sorted(ev[i].elapsed_time(ev[i + 1]) for i in range(steps))[steps // 2]
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        host_out.copy_(eng.vocoder(host_mel.to("cuda:0", non_blocking=True)), non_blocking=True)
+        torch.cuda.synchronize()
+    ms_e2e = (time.perf_counter() - t0) / steps * 1e3
+    print(json.dumps({"metric": METRIC, "value": 10.0 / (ms * 1e-3), "unit": UNIT, "n_gpus": 1, "steps": steps, "warmup": warm,
+                      "ms_per_step": ms, "higher_is_better": True, "data": "synthetic",
+                      "dtype": "bf16" if args.precision == "bf16" else "f32",
+                      "config": {"workload": "configs[1]: Vocoder.forward on 1 x 10 s linear 128-bin mel (1001 frames -> 443646 samples), "
+                                             "batch 1 latency, median of the timed steps, 1 GPU", "precision": args.precision},
+                      "e2e": {"value": 10.0 / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e,
+                              "h2d_bytes_per_step": host_mel.numel() * 4, "d2h_bytes_per_step": host_out.numel() * 4}}))
+
+
 def run_torch_gpu(args):
     """Library baseline: the reference's op sequence (oracle restatement: F.conv1d/conv2d/conv_transpose, batch_norm,
     matmul-based GRU loop) executed by stock PyTorch on cuda:0 with its defaults (TF32 convolutions through cuDNN).
@@ -274,8 +312,9 @@ def main():
                     help="bf16 = tcgen05 tensor-core path (default); fp32 = SIMT validation path")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch the ~360 kernels of a step individually")
-    ap.add_argument("--workload", default="batch", choices=["batch", "longform"],
-                    help="batch: configs[2] (default); longform: configs[4], one 10 min utterance = 20 x 30 s segments, 1 GPU")
+    ap.add_argument("--workload", default="batch", choices=["batch", "longform", "vocoder"],
+                    help="batch: configs[2] (default); longform: configs[4], one 10 min utterance = 20 x 30 s segments, 1 GPU; "
+                         "vocoder: configs[1], Vocoder.forward on one 10 s 128-bin mel (synthesis-only latency), 1 GPU")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -283,6 +322,8 @@ def main():
         return run_torch_gpu(args)
     if args.workload == "longform":
         return run_longform(args)
+    if args.workload == "vocoder":
+        return run_vocoder(args)
     args.warmup = max(args.warmup, 3)
 
     import torch.distributed as dist
