@@ -142,7 +142,8 @@ class Engine:
     # ------------------------------------------------------------------ workspace
     def _workspace(self, nbytes):
         if nbytes == 0:
-            raise _lib.VfxError("workspace query failed: " + self.lib.vfx_last_error().decode())
+            raise _lib.VfxError("workspace query returned 0: the shape is out of range (restore() needs L > 1024 samples) or this "
+                                "engine holds the vocoder weights only (stand-alone Vocoder: restore/analysis are unavailable)")
         if self._ws is None or self._ws.numel() < nbytes:
             self._ws = None
             self._ws = torch.empty(nbytes, dtype=torch.uint8, device=f"cuda:{self.device}")
