@@ -1,6 +1,8 @@
 """CPU tests: the oracle restatement against the golden vectors produced by the UNMODIFIED
 reference (tests/golden/make_golden.py), plus the length arithmetic pinned by the reference's
 own FLAC fixtures."""
+import os
+
 import numpy as np
 import torch
 import pytest
@@ -99,3 +101,21 @@ def test_slaney_basis_matches_torchaudio_formula():
     enorm = 2.0 / (f_pts[2:130] - f_pts[:128])
     ref = (fb * enorm[None, :]).t().numpy()
     assert np.max(np.abs(O.slaney_htk_mel_basis() - ref)) < 2e-6
+
+
+@pytest.mark.timeout(900)
+@pytest.mark.skipif(not os.path.isdir("/root/reference/voicefixer"), reason="reference checkout not present (GPU box)")
+def test_oracle_live_against_unmodified_reference_on_fresh_inputs():
+    """tests/golden/live_pin.py: the unmodified reference (its own VoiceFixer() / Vocoder() loading seeded synthetic
+    checkpoints) against the oracle on inputs that are not in the committed fixtures -- analysis at the 64-frame grid
+    edges, vocoder at odd / even T, restore_inmem modes 0 and 2 (with the dropout masks the reference drew), and the
+    your_vocoder_func hook.  Run in a subprocess: the stub-loader registers a `voicefixer` namespace package."""
+    import json, subprocess, sys
+    script = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "live_pin.py")
+    r = subprocess.run([sys.executable, script, "9100"], capture_output=True, text=True, timeout=850)
+    assert r.returncode == 0, r.stderr[-3000:]
+    rep = json.loads(r.stdout.strip().splitlines()[-1])
+    assert set(rep) >= {"analysis_T2", "analysis_T64", "analysis_T128", "analysis_T257", "vocoder_T5", "vocoder_T12",
+                        "restore_mode0_1.3s", "restore_mode2_1.6s", "hook_mel", "hook_out"}
+    for k, v in rep.items():
+        assert v < (2e-5 if k != "hook_mel" else 5e-5), (k, v)             # fp32 restatement: same ops, same order
