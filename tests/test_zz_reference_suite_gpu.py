@@ -68,3 +68,34 @@ def test_reference_acceptance_script(tmp_path, monkeypatch, states, precision):
     vocoder.oracle(fpath=p360, out_path=out, cuda=True)
     assert samples_in(out) == 97902
     check(out, str(utt / "target" / "oracle.flac"))
+
+
+@pytest.mark.timeout(300)
+def test_your_vocoder_func_hook(tmp_path, monkeypatch, states):
+    """base.py:126-129 / README "use your own vocoder": the callback receives the restored LINEAR mel [B, 1, T, 128] and
+    returns a waveform [B, 1, S]; the result is energy-clamped and centre-trimmed like the built-in vocoder's."""
+    import torch
+    from voicefixer import VoiceFixer
+    from voicefixer_b200 import synthetic
+    from oracle import vf_oracle as O
+    monkeypatch.setenv("HOME", str(tmp_path))
+    synthetic.write_checkpoints(str(tmp_path), seed=0)
+    vf = VoiceFixer(precision="fp32")
+    wav = synthetic.make_utterances(1, seconds=0.8, seed=61)[0]
+    seen = {}
+
+    def half_gain_vocoder(mel):
+        seen["mel"] = mel.detach().float().cpu()
+        return vf._model.vocoder(mel, cuda=True) * 0.5                  # the built-in Vocoder.forward at half gain
+
+    out = vf.restore_inmem(wav, cuda=True, mode=0, your_vocoder_func=half_gain_vocoder)
+    base = vf.restore_inmem(wav, cuda=True, mode=0)
+    T = 1 + wav.shape[0] // 441
+    assert tuple(seen["mel"].shape) == (1, 1, T, 128) and out.shape == base.shape == (1, wav.shape[0])
+    _, mel = O.frontend(torch.from_numpy(wav)[None], states[0])
+    ref_mel = O.from_log(O.analysis(mel, states[0]))
+    rel = lambda a, b: float(np.sqrt(np.mean((np.asarray(a, np.float64) - np.asarray(b, np.float64)) ** 2)) / np.sqrt(np.mean(np.asarray(b, np.float64) ** 2)))
+    assert rel(seen["mel"].numpy(), ref_mel.numpy()) < 1e-3            # 10**x amplifies the 1e-4 log-mel tolerance
+    assert rel(out, 0.5 * base) < 1e-3                                  # log -> 10**x -> log10 round trip in the hook path
+    loud = vf.restore_inmem(wav, cuda=True, mode=0, your_vocoder_func=lambda m: vf._model.vocoder(m, cuda=True) * 40.0)
+    assert np.abs(loud).max() <= 1.0 + 1e-6                            # base.py:131-133 energy clamp
