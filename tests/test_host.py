@@ -332,3 +332,50 @@ def test_cli_main_wiring_folder_mode_all_with_flac_output(tmp_path, monkeypatch,
     assert cli.main(["-i", str(tmp_path / "in" / "b.wav"), "-o", str(tmp_path / "x" / "b.flac"), "--silent"]) == 0
     assert (tmp_path / "x" / "b.flac").read_bytes()[:4] == b"fLaC"
     assert wavio.load_mono(str(tmp_path / "x" / "b.flac")).shape == (7000,)
+
+
+def test_wav_reader_formats_beyond_stdlib_wave(tmp_path):
+    """librosa.load accepts float and WAVE_FORMAT_EXTENSIBLE files; stdlib `wave` rejects them.  All decode to the same
+    float32 samples (to the format's resolution), extra chunks and odd padding are skipped."""
+    import struct
+    from voicefixer_b200 import wavio
+    rng = np.random.default_rng(2)
+    x = np.clip(0.4 * rng.standard_normal((1000, 2)), -0.999, 0.999)
+
+    def riff(tag, bits, payload, extensible=False, extra=b"", data_size=None):
+        nch, sr = 2, 44100
+        block = nch * bits // 8
+        if extensible:
+            fmt = struct.pack("<HHIIHHHHIH14s", 0xFFFE, nch, sr, sr * block, block, bits, 22, bits, 3, tag,
+                              bytes.fromhex("000000001000800000aa00389b71"))
+        else:
+            fmt = struct.pack("<HHIIHH", tag, nch, sr, sr * block, block, bits)
+        body = b"WAVE" + b"fmt " + struct.pack("<I", len(fmt)) + fmt + extra
+        body += b"data" + struct.pack("<I", len(payload) if data_size is None else data_size) + payload
+        return b"RIFF" + struct.pack("<I", len(body)) + body
+
+    i24 = np.round(x * 8388607).astype(np.int32)
+    b24 = np.stack([(i24 >> s) & 0xFF for s in (0, 8, 16)], axis=-1).astype(np.uint8).tobytes()
+    cases = {
+        "f32": (riff(3, 32, x.astype("<f4").tobytes()), 1e-7),
+        "f64": (riff(3, 64, x.astype("<f8").tobytes()), 1e-7),
+        "f32ext": (riff(3, 32, x.astype("<f4").tobytes(), extensible=True), 1e-7),
+        "i16ext": (riff(1, 16, np.round(x * 32767).astype("<i2").tobytes(), extensible=True), 1e-4),
+        "i24": (riff(1, 24, b24), 1e-6),
+        "i32": (riff(1, 32, np.round(x * 2147483647).astype("<i4").tobytes()), 1e-6),
+        "u8": (riff(1, 8, np.round(x * 127 + 128).astype(np.uint8).tobytes()), 2e-2),
+        "list_chunk": (riff(3, 32, x.astype("<f4").tobytes(), extra=b"LIST" + struct.pack("<I", 5) + b"abcde\x00"), 1e-7),
+        "streamed": (riff(3, 32, x.astype("<f4").tobytes(), data_size=0xFFFFFFFF), 1e-7),
+    }
+    for name, (blob, tol) in cases.items():
+        p = tmp_path / f"{name}.wav"
+        p.write_bytes(blob)
+        y = wavio.read_wave(str(p), 44100)
+        assert y.dtype == np.float32 and y.shape == (1000, 2) and np.abs(y - x).max() < tol, name
+        assert wavio.load_mono(str(p)).shape == (1000,)
+    (tmp_path / "bad.wav").write_bytes(riff(2, 4, bytes(100)))                 # ADPCM
+    with pytest.raises(RuntimeError, match="unsupported WAVE format"):
+        wavio.load_mono(str(tmp_path / "bad.wav"))
+    (tmp_path / "junk.wav").write_bytes(b"OggS" + bytes(64))
+    with pytest.raises(RuntimeError, match="not a RIFF/WAVE"):
+        wavio.load_mono(str(tmp_path / "junk.wav"))

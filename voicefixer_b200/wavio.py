@@ -15,22 +15,60 @@ def _read_pcm(path):
         with open(str(path), "rb") as f:
             pcm, sr, bps = _hostio.flac_decode(f.read())
         return pcm.astype(np.float32) / np.float32(1 << (bps - 1)), sr
-    with wave.open(str(path), "rb") as f:
-        nch, sw, sr, nfr = f.getnchannels(), f.getsampwidth(), f.getframerate(), f.getnframes()
-        raw = f.readframes(nfr)
-    if sw == 2:
-        x = np.frombuffer(raw, dtype="<i2").astype(np.float32) / 32768.0
-    elif sw == 4:
-        x = np.frombuffer(raw, dtype="<i4").astype(np.float32) / 2147483648.0
-    elif sw == 1:
-        x = (np.frombuffer(raw, dtype=np.uint8).astype(np.float32) - 128.0) / 128.0
-    elif sw == 3:
-        b = np.frombuffer(raw, dtype=np.uint8).reshape(-1, 3).astype(np.int32)
+    return _read_riff(path)
+
+
+def _read_riff(path):
+    """RIFF/WAVE reader for what librosa.load (libsndfile) accepts on this path and stdlib `wave` does not: besides
+    integer PCM of 8 / 16 / 24 / 32 bits also IEEE float 32 / 64 (format tag 3) and WAVE_FORMAT_EXTENSIBLE (0xFFFE,
+    sub-format in the first two bytes of the GUID); odd-sized chunks are padded, unknown chunks skipped, a `data` size
+    of 0 / 0xFFFFFFFF (streamed writers) means "to the end of the file"."""
+    import struct
+    with open(str(path), "rb") as f:
+        blob = f.read()
+    if len(blob) < 12 or blob[:4] != b"RIFF" or blob[8:12] != b"WAVE":
+        raise RuntimeError(f"{path}: not a RIFF/WAVE file")
+    pos, fmt, data = 12, None, None
+    while pos + 8 <= len(blob):
+        cid, size = blob[pos:pos + 4], struct.unpack("<I", blob[pos + 4:pos + 8])[0]
+        body = pos + 8
+        if cid == b"fmt ":
+            if size < 16:
+                raise RuntimeError(f"{path}: short fmt chunk")
+            tag, nch, sr, _, _, bits = struct.unpack("<HHIIHH", blob[body:body + 16])
+            if tag == 0xFFFE and size >= 26:
+                tag = struct.unpack("<H", blob[body + 24:body + 26])[0]
+            fmt = (tag, nch, sr, bits)
+        elif cid == b"data":
+            if size in (0, 0xFFFFFFFF) or body + size > len(blob):
+                size = len(blob) - body
+            data = blob[body:body + size]
+            break
+        pos = body + size + (size & 1)
+    if fmt is None or data is None:
+        raise RuntimeError(f"{path}: missing fmt or data chunk")
+    tag, nch, sr, bits = fmt
+    if nch < 1 or sr < 1:
+        raise RuntimeError(f"{path}: invalid channel count / sample rate")
+    width = (bits + 7) // 8
+    data = data[: len(data) // (width * nch) * (width * nch)]
+    if tag == 1 and bits == 16:
+        x = np.frombuffer(data, dtype="<i2").astype(np.float32) / 32768.0
+    elif tag == 1 and bits == 32:
+        x = (np.frombuffer(data, dtype="<i4").astype(np.float64) / 2147483648.0).astype(np.float32)
+    elif tag == 1 and bits == 8:
+        x = (np.frombuffer(data, dtype=np.uint8).astype(np.float32) - 128.0) / 128.0
+    elif tag == 1 and bits == 24:
+        b = np.frombuffer(data, dtype=np.uint8).reshape(-1, 3).astype(np.int32)
         v = b[:, 0] | (b[:, 1] << 8) | (b[:, 2] << 16)
         v = np.where(v >= 1 << 23, v - (1 << 24), v)
         x = v.astype(np.float32) / 8388608.0
+    elif tag == 3 and bits == 32:
+        x = np.frombuffer(data, dtype="<f4").astype(np.float32)
+    elif tag == 3 and bits == 64:
+        x = np.frombuffer(data, dtype="<f8").astype(np.float32)
     else:
-        raise RuntimeError(f"unsupported sample width {sw}")
+        raise RuntimeError(f"{path}: unsupported WAVE format (tag {tag}, {bits} bits); PCM 8/16/24/32 and float 32/64 are read")
     return x.reshape(-1, nch), sr
 
 
