@@ -285,3 +285,49 @@ def test_decode_rejects_reserved_fields():
     with pytest.raises(RuntimeError, match="channel"):                                                      # 2 channels in a mono stream
         fr = W.frame(0, 192, 1, 16, [lambda b: W.sub_verbatim(b, x, 16)] * 2)
         _hostio.flac_decode(W.stream([fr], 44100, 1, 16, 192, x))
+
+
+def test_flac_roundtrip_property_random_walks():
+    """Property test (hypothesis): any int16 signal of any length / channel count / rate survives encode -> decode
+    bit-exactly, the STREAMINFO signature matches hashlib, and truncating the stream anywhere is detected."""
+    from hypothesis import given, settings, strategies as st
+    from voicefixer_b200 import _hostio
+
+    @settings(max_examples=60, deadline=None)
+    @given(st.integers(0, 9000), st.integers(1, 3), st.integers(0, 2 ** 31 - 1), st.sampled_from([1, 7, 300, 5000, 40000]),
+           st.sampled_from([8000, 22050, 44100, 48000, 12345]))
+    def check(n, ch, seed, step, sr):
+        rng = np.random.default_rng(seed)
+        x = np.clip(np.cumsum(rng.integers(-step, step + 1, (n, ch)), axis=0), -32768, 32767).astype(np.int16)
+        data = _hostio.flac_encode_int16(x, sr)
+        y, got_sr, bps = _hostio.flac_decode(data)
+        assert got_sr == sr and bps == 16 and y.shape == (n, ch) and np.array_equal(y, x)
+        assert bytes(_hostio.flac_info(data).md5) == hashlib.md5(x.astype("<i2").tobytes()).digest()
+        if n > 0:
+            cut = 42 + int(rng.integers(0, len(data) - 42))
+            with pytest.raises(RuntimeError):
+                _hostio.flac_decode(data[:cut])
+
+    check()
+
+
+def test_decoder_survives_random_corruption():
+    """Bit flips and truncation of valid streams either decode or raise RuntimeError -- never crash the process
+    (tools/fuzz_flac.c is the long-running version under ASan / UBSan, including CRC-repaired corruptions)."""
+    from voicefixer_b200 import _hostio
+    rng = np.random.default_rng(99)
+    g = np.load(os.path.join(ROOT, "tests", "golden", "flac_libflac_excerpt.npz"))
+    seeds = [g["flac"].tobytes(), _hostio.flac_encode_int16(rng.integers(-3000, 3000, (6000, 2)).astype(np.int16), 44100)]
+    outcomes = {"ok": 0, "rejected": 0}
+    for it in range(400):
+        data = bytearray(seeds[it % 2])
+        for _ in range(int(rng.integers(1, 5))):
+            data[int(rng.integers(0, len(data)))] ^= 1 << int(rng.integers(0, 8))
+        if it % 4 == 0:
+            data = data[: int(rng.integers(0, len(data)))]
+        try:
+            _hostio.flac_decode(bytes(data))
+            outcomes["ok"] += 1
+        except RuntimeError:
+            outcomes["rejected"] += 1
+    assert outcomes["rejected"] > 300

@@ -272,6 +272,8 @@ static int decode_residual(BitReader* br, int64_t* x, int blocksize, int order) 
   return VFX_IO_OK;
 }
 
+#define U(v) ((uint64_t)(v))
+
 static int decode_subframe(BitReader* br, int64_t* x, int blocksize, int bps) {
   if (br_bits(br, 1)) return fail(VFX_IO_ERR_FORMAT, "flac: subframe padding bit set");
   const int type = (int)br_bits(br, 6);
@@ -290,11 +292,13 @@ static int decode_subframe(BitReader* br, int64_t* x, int blocksize, int bps) {
     if (order > blocksize) return fail(VFX_IO_ERR_FORMAT, "flac: fixed order %d > blocksize %d", order, blocksize);
     for (int i = 0; i < order; ++i) x[i] = br_signed(br, bps);
     if ((rc = decode_residual(br, x, blocksize, order)) != VFX_IO_OK) return rc;
+    /* the recursions run in unsigned arithmetic: a corrupt (but CRC-valid) stream may drive them past 2^63, which
+     * must wrap, not be undefined; for a valid stream every intermediate fits and the result is identical */
     switch (order) {
-      case 1: for (int i = 1; i < blocksize; ++i) x[i] += x[i - 1]; break;
-      case 2: for (int i = 2; i < blocksize; ++i) x[i] += 2 * x[i - 1] - x[i - 2]; break;
-      case 3: for (int i = 3; i < blocksize; ++i) x[i] += 3 * x[i - 1] - 3 * x[i - 2] + x[i - 3]; break;
-      case 4: for (int i = 4; i < blocksize; ++i) x[i] += 4 * x[i - 1] - 6 * x[i - 2] + 4 * x[i - 3] - x[i - 4]; break;
+      case 1: for (int i = 1; i < blocksize; ++i) x[i] = (int64_t)(U(x[i]) + U(x[i - 1])); break;
+      case 2: for (int i = 2; i < blocksize; ++i) x[i] = (int64_t)(U(x[i]) + 2 * U(x[i - 1]) - U(x[i - 2])); break;
+      case 3: for (int i = 3; i < blocksize; ++i) x[i] = (int64_t)(U(x[i]) + 3 * U(x[i - 1]) - 3 * U(x[i - 2]) + U(x[i - 3])); break;
+      case 4: for (int i = 4; i < blocksize; ++i) x[i] = (int64_t)(U(x[i]) + 4 * U(x[i - 1]) - 6 * U(x[i - 2]) + 4 * U(x[i - 3]) - U(x[i - 4])); break;
       default: break;
     }
   } else if (type >= 32) {                          /* LPC, order = type - 31 */
@@ -309,9 +313,9 @@ static int decode_subframe(BitReader* br, int64_t* x, int blocksize, int bps) {
     for (int j = 0; j < order; ++j) coef[j] = br_signed(br, prec);
     if ((rc = decode_residual(br, x, blocksize, order)) != VFX_IO_OK) return rc;
     for (int i = order; i < blocksize; ++i) {
-      int64_t acc = 0;
-      for (int j = 0; j < order; ++j) acc += coef[j] * x[i - 1 - j];
-      x[i] += acc >> shift;
+      uint64_t acc = 0;
+      for (int j = 0; j < order; ++j) acc += U(coef[j]) * U(x[i - 1 - j]);
+      x[i] = (int64_t)(U(x[i]) + U((int64_t)acc >> shift));
     }
   } else {
     return fail(VFX_IO_ERR_FORMAT, "flac: reserved subframe type %d", type);
@@ -399,13 +403,13 @@ long long vfx_flac_decode(const uint8_t* data, size_t nbytes, int32_t* pcm, size
     off += body_len + 2;
 
     int64_t *c0 = sub, *c1 = sub + 65536u;
-    if (ch_code == 8) for (int i = 0; i < blocksize; ++i) c1[i] = c0[i] - c1[i];            /* left, side  */
-    else if (ch_code == 9) for (int i = 0; i < blocksize; ++i) c0[i] = c0[i] + c1[i];       /* side, right */
+    if (ch_code == 8) for (int i = 0; i < blocksize; ++i) c1[i] = (int64_t)(U(c0[i]) - U(c1[i]));   /* left, side  */
+    else if (ch_code == 9) for (int i = 0; i < blocksize; ++i) c0[i] = (int64_t)(U(c0[i]) + U(c1[i])); /* side, right */
     else if (ch_code == 10)
       for (int i = 0; i < blocksize; ++i) {                                                  /* mid, side   */
-        const int64_t s = c1[i], m = (int64_t)((uint64_t)c0[i] << 1) | (s & 1);
-        c0[i] = (m + s) >> 1;
-        c1[i] = (m - s) >> 1;
+        const int64_t s = c1[i], m = (int64_t)(U(c0[i]) << 1) | (s & 1);
+        c0[i] = (int64_t)(U(m) + U(s)) >> 1;
+        c1[i] = (int64_t)(U(m) - U(s)) >> 1;
       }
     size_t take = (size_t)blocksize;
     if (info.total_samples && done + take > info.total_samples) take = (size_t)(info.total_samples - done);
