@@ -196,12 +196,23 @@ def run_longform(args):
     for _ in range(args.steps):
         run()
     dt = (time.perf_counter() - t0) / args.steps
+    # time to the FIRST restored 30 s segment when the caller wants audio as early as possible: segment 0 alone
+    # (host in -> host out), the remaining 19 would follow as a second batch
+    first_ms = None
+    try:
+        for _ in range(3):
+            t1 = time.perf_counter()
+            host_out[:1].copy_(eng.restore(host_in[:1].to("cuda:0", non_blocking=True), mode=0), non_blocking=True)
+            torch.cuda.synchronize()
+            first_ms = (time.perf_counter() - t1) * 1e3
+    except Exception as e:                                            # informational only
+        first_ms = f"{type(e).__name__}: {e}"
     print(json.dumps({"metric": METRIC, "value": 600.0 / dt, "unit": UNIT, "n_gpus": 1, "steps": args.steps,
                       "warmup": max(args.warmup, 2), "ms_per_step": dt * 1e3, "higher_is_better": True, "data": "synthetic",
                       "dtype": "bf16" if args.precision == "bf16" else "f32",
                       "config": {"workload": "configs[4]: 1 x 10 min utterance = 20 x 30 s segments (T=3001 frames each), mode 0, "
                                              "host numpy in -> host numpy out, 1 GPU", "precision": args.precision,
-                                 "latency_to_full_waveform_ms": dt * 1e3,
+                                 "latency_to_full_waveform_ms": dt * 1e3, "latency_to_first_segment_ms": first_ms,
                                  "workspace_gb": eng.workspace_bytes(20, seg) / 1e9}}))
 
 
