@@ -22,7 +22,9 @@ def _stream():
 
 
 def default_precision():
-    return os.environ.get("VFX_PRECISION", "fp32")
+    """"bf16" (tcgen05 tensor-core path, the production mode: meets the reference's own 1e-2 mean-abs acceptance bar with 4x
+    margin) unless VFX_PRECISION=fp32 selects the SIMT fp32 validation path (reference-exact to ~4e-6 relative RMS)."""
+    return os.environ.get("VFX_PRECISION", "bf16")
 
 
 class Planner:
