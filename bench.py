@@ -528,7 +528,7 @@ def main():
         print(json.dumps({
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
+            "vs_baseline": None, "dtype": {"bf16": "bf16", "tf32": "tf32", "fp32": "f32"}[args.precision], "data": "synthetic",
             "config": {"workload": f"configs[2]: batch {B} x {args.seconds:g} s synthetic degraded 44.1 kHz mono "
                                    f"utterances per GPU, mode 0, seeded synthetic checkpoints",
                        "precision": args.precision, "global_batch": world * B,

@@ -30,9 +30,14 @@ enum vfx_status {
   VFX_ERR_UNSUPPORTED = -5
 };
 
-/* Arithmetic of the convolution GEMMs. FP32: SIMT fp32 FMA (validation path, bit-for-bit
- * deterministic).  BF16: tcgen05 tensor-core MMA, bf16 operands, fp32 accumulation in TMEM. */
-enum vfx_precision { VFX_PREC_FP32 = 0, VFX_PREC_BF16 = 1 };
+/* Arithmetic of the convolution GEMMs.
+ *   FP32: SIMT fp32 FMA (validation path, bit-for-bit deterministic).
+ *   BF16: tcgen05 tensor-core MMA (kind::f16), bf16 operands and weights, fp32 accumulation in TMEM.
+ *   TF32: tcgen05 tensor-core MMA (kind::tf32), fp32 storage with operands and weights rounded to tf32
+ *         (round-to-nearest) by their producers, fp32 accumulation -- the arithmetic of the reference's own
+ *         CUDA path (torch.backends.cudnn.allow_tf32 defaults to True; the reference's test/test.py:27-35
+ *         compares that path with its CPU path).  Weights are registered in the FP32 layout. */
+enum vfx_precision { VFX_PREC_FP32 = 0, VFX_PREC_BF16 = 1, VFX_PREC_TF32 = 2 };
 
 /* restore() modes, voicefixer/base.py:110-115. mode 1's pre-filter is vfx_hf_cut(). */
 enum vfx_mode { VFX_MODE_EVAL = 0, VFX_MODE_TRAIN_BN = 2 };
@@ -52,7 +57,7 @@ int vfx_engine_destroy(vfx_engine* e);
  * against what the engine expects when it is first used).  Names and layouts: DESIGN.md §3.
  * Replaces torch.load + load_state_dict: voicefixer/base.py:15-30, voicefixer/vocoder/base.py:24-32. */
 int vfx_engine_set_tensor(vfx_engine* e, const char* name, const void* dev_ptr, size_t bytes);
-/* Engine options: "use_tc" (BF16 only; 1 = tcgen05 kernel [default], 0 = SIMT cross-check),
+/* Engine options: "use_tc" (BF16 / TF32; 1 = tcgen05 kernel [default], 0 = SIMT cross-check on the same operands),
  * "profile" (0/1, see vfx_profile_report). */
 int vfx_engine_set_option(vfx_engine* e, const char* key, int value);
 /* Number of CUDA kernels this library has launched in this process (bench.py's gpu_launches). */
@@ -149,7 +154,7 @@ typedef struct vfx_conv_desc {
 enum vfx_act { VFX_ACT_NONE = 0, VFX_ACT_LRELU = 1, VFX_ACT_ELU = 2,
                VFX_ACT_LRELU_XSINX = 3 /* v = lrelu(x, p); v + sin v */, VFX_ACT_SIGMOID = 4 };
 
-/* impl: 0 = SIMT, 1 = tcgen05 (BF16 only). */
+/* impl: 0 = SIMT, 1 = tcgen05 (BF16 or TF32). */
 int vfx_conv_gemm(int precision, int impl, const vfx_conv_desc* d, void* stream);
 
 /* One direction-pair GRU layer recurrence: gi[B][T][2][768] (x W_ih^T + b_ih, fwd|bwd),

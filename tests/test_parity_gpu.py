@@ -91,6 +91,54 @@ def test_api_dropin_restore_inmem_and_segmentation(tmp_path, monkeypatch, states
     assert rel_rms(w.cpu().numpy(), gv["out"]) < TOL_WAV
 
 
+# ---------------------------------------------------------------------------- BASELINE sizes, asserting
+# One 10 s utterance (T = 1001 frames, BASELINE configs[2] item size) and one 30 s segment (T = 3001, the segment
+# size of restore_inmem, voicefixer/base.py:116) against the CPU oracle on the same input and checkpoints, in every
+# precision.  Frozen after measurement on B200 (tools/measure_parity.py; CPU prediction of the operand-rounding
+# error alone, tools/sim_precision.py: tf32 1.7e-3, bf16 1.3e-2 relative RMS):
+#   fp32   rel-RMS 2e-4
+#   tf32   rel-RMS 2.5e-3, mean-abs 1e-3    (SURVEY 8d pencilled 2e-3 "to be confirmed by measurement")
+#   bf16   rel-RMS 3e-2,   mean-abs 5e-3    (reference's own CPU<->GPU acceptance bar: mean-abs 1e-2, test/test.py:35)
+FULL_TOL = {"fp32": (2e-4, 1e-4), "tf32": (2.5e-3, 1e-3), "bf16": (3e-2, 5e-3)}
+
+
+@pytest.fixture(scope="module")
+def oracle_10s(states):
+    from voicefixer_b200 import synthetic
+    from oracle import vf_oracle as O
+    wav = synthetic.make_utterances(1, seconds=10.0, seed=1234)[0]
+    return wav, O.restore_inmem(wav, states[0], states[1], mode=0)
+
+
+@pytest.mark.timeout(600)
+@pytest.mark.parametrize("prec", ["fp32", "tf32", "bf16"])
+def test_restore_10s_vs_oracle(states, oracle_10s, prec):
+    from voicefixer_b200.engine import Engine
+    wav, ref = oracle_10s
+    assert 1 + wav.shape[0] // 441 == 1001
+    out = Engine(states[0], states[1], precision=prec).restore(wav[None]).cpu().numpy()
+    tol_rms, tol_mae = FULL_TOL[prec]
+    assert out.shape == ref.shape
+    assert rel_rms(out, ref) < tol_rms
+    assert float(np.mean(np.abs(out - ref))) < tol_mae
+
+
+@pytest.mark.timeout(900)
+def test_restore_30s_segment_vs_oracle(states):
+    """T = 3001: one full restore_inmem segment, tensor-core precisions."""
+    from voicefixer_b200 import synthetic
+    from voicefixer_b200.engine import Engine
+    from oracle import vf_oracle as O
+    wav = synthetic.make_utterances(1, seconds=30.0, seed=4321)[0]
+    assert 1 + wav.shape[0] // 441 == 3001
+    ref = O.restore_inmem(wav, states[0], states[1], mode=0)
+    for prec in ("tf32", "bf16"):
+        out = Engine(states[0], states[1], precision=prec).restore(wav[None]).cpu().numpy()
+        tol_rms, tol_mae = FULL_TOL[prec]
+        assert rel_rms(out, ref) < tol_rms, prec
+        assert float(np.mean(np.abs(out - ref))) < tol_mae, prec
+
+
 def test_full_size_properties(engine):
     """BASELINE config sizes (10 s items): output length, finiteness, |y| <= 1, batch
     permutation equivariance (a size-independent property of independent items)."""
@@ -155,6 +203,59 @@ def test_bf16_mode2_vs_reference_golden(engine_bf16):
     masks = torch.stack([torch.from_numpy(np.unpackbits(g[k])[: T * 512].reshape(1, T, 512)) for k in ("mask0", "mask1")])
     out = engine_bf16.analysis(g["mel"][:, 0], mode=2, drop_masks=masks)
     assert rel_rms(out.cpu().numpy(), g["out"][:, 0]) < 3e-2
+
+
+# ---------------------------------------------------------------------------- tf32 tensor-core path
+# precision "tf32": tcgen05 kind::tf32 on fp32 storage, every operand rounded to tf32 by its producer, fp32
+# accumulation -- the arithmetic class of the reference's own CUDA path (cuDNN TF32 convolutions).
+TOL_TF32_STAGE, TOL_TF32_WAV, TOL_TF32_MAE = 2e-3, 2.5e-3, 1e-3
+
+
+@pytest.fixture(scope="module")
+def engine_tf32(states):
+    from voicefixer_b200.engine import Engine
+    return Engine(states[0], states[1], precision="tf32")
+
+
+@pytest.mark.parametrize("T", [1, 63, 65, 130])
+def test_tf32_analysis_vs_reference_golden(engine_tf32, T):
+    g = golden(f"analysis_T{T}")
+    assert rel_rms(engine_tf32.analysis(g["mel"][:, 0]).cpu().numpy(), g["out"][:, 0]) < TOL_TF32_STAGE
+
+
+@pytest.mark.parametrize("T", [3, 20])
+def test_tf32_vocoder_vs_reference_golden(engine_tf32, T):
+    g = golden(f"vocoder_T{T}")
+    out = engine_tf32.vocoder(g["mel"][:, 0]).cpu().numpy()
+    assert rel_rms(out, g["out"][:, 0]) < TOL_TF32_WAV
+    assert float(np.mean(np.abs(out - g["out"][:, 0]))) < TOL_TF32_MAE
+
+
+def test_tf32_restore_vs_reference_golden(engine_tf32):
+    g = golden("restore_mode0")
+    out = engine_tf32.restore(g["wav"][None]).cpu().numpy()
+    assert rel_rms(out, g["out"]) < TOL_TF32_WAV
+    assert float(np.mean(np.abs(out - g["out"]))) < TOL_TF32_MAE
+
+
+def test_tf32_tensor_core_path_equals_simt_on_same_operands(engine_tf32):
+    """tf32 x tf32 products are exact in fp32: the SIMT kernel on the same rounded operands differs from the tcgen05
+    kernel only by accumulation order and the fast-math activations, far below the tf32 rounding noise."""
+    from voicefixer_b200 import synthetic
+    wav = synthetic.make_utterances(2, seconds=0.5, seed=13)
+    y_tc = engine_tf32.restore(wav).cpu().numpy()
+    engine_tf32.set_option("use_tc", 0)
+    y_simt = engine_tf32.restore(wav).cpu().numpy()
+    engine_tf32.set_option("use_tc", 1)
+    assert rel_rms(y_tc, y_simt) < TOL_TF32_WAV
+
+
+def test_tf32_mode2_vs_reference_golden(engine_tf32):
+    g = golden("analysis_mode2")
+    T = g["mel"].shape[2]
+    masks = torch.stack([torch.from_numpy(np.unpackbits(g[k])[: T * 512].reshape(1, T, 512)) for k in ("mask0", "mask1")])
+    out = engine_tf32.analysis(g["mel"][:, 0], mode=2, drop_masks=masks)
+    assert rel_rms(out.cpu().numpy(), g["out"][:, 0]) < 4e-3
 
 
 def test_cuda_graph_replay_matches_direct_launch(engine_bf16):

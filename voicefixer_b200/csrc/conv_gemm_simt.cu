@@ -10,7 +10,7 @@
 //   Linear / GRU W_ih     voicefixer/restorer/model.py:71-98,35-42
 //   Conv1d k3/k7 dilated  voicefixer/vocoder/model/generator.py:33-54,75,96; modules.py:550-576
 //   ConvTranspose1d       voicefixer/vocoder/model/modules.py:451-459 (u output phases, 2 taps each)
-// With bf16 operands it reproduces the tensor-core path's arithmetic (bf16 x bf16 products are
+// With bf16 (or tf32-rounded) operands it reproduces the tensor-core path's arithmetic (the products are
 // exact in fp32) and is used by tests to cross-check the tcgen05 kernel.
 #include "vfx_common.cuh"
 
@@ -24,6 +24,13 @@ template <typename T> struct Vec8;   // 8 consecutive operand elements
 template <> struct Vec8<float> {
   float v[8];
   __device__ void load(const float* p) {
+    float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+  }
+};
+template <> struct Vec8<tf32_t> {
+  float v[8];
+  __device__ void load(const tf32_t* p) {
     float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
     v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
   }
@@ -164,6 +171,8 @@ int conv_gemm_simt(int precision, const vfx_conv_desc& d, cudaStream_t st) {
                 ((uintptr_t)d.a % 16 == 0);
   if (precision == VFX_PREC_BF16)
     conv_gemm_simt_kernel<__nv_bfloat16><<<grid, NT, 0, st>>>(d, vec_ok);
+  else if (precision == VFX_PREC_TF32)     // fp32 FMA on tf32-rounded operands (products exact): same arithmetic as kind::tf32
+    conv_gemm_simt_kernel<tf32_t><<<grid, NT, 0, st>>>(d, vec_ok);
   else
     conv_gemm_simt_kernel<float><<<grid, NT, 0, st>>>(d, vec_ok);
   VFX_LAUNCH_CHECK();

@@ -1,5 +1,10 @@
 // Channels-last shifted-window convolution GEMM on the 5th-gen tensor cores (sm_100a):
-// TMA-staged bf16 tiles -> tcgen05.mma (fp32 accumulators in TMEM) -> fused epilogue.
+// TMA-staged operand tiles -> tcgen05.mma (fp32 accumulators in TMEM) -> fused epilogue.
+// Two operand formats, same kernel (template parameter TF32):
+//   VFX_PREC_BF16  bf16 operands / weights, kind::f16, UMMA K = 16, K chunk = 64 channels (32 if Cin == 32)
+//   VFX_PREC_TF32  fp32 storage rounded to tf32 by the producers, kind::tf32, UMMA K = 8, K chunk = 32 channels
+// (a K chunk is one swizzled 128-byte row -- 64 bytes for the bf16 Cin == 32 case -- so every piece of address
+// arithmetic below is in bytes and shared by both formats; one MMA always advances 32 bytes along K).
 //
 // Same contract as conv_gemm_simt (vfx_conv_desc); this is the production path behind the
 // reference's Conv1d / Conv2d / ConvTranspose / Linear layers (file:line list in conv_gemm_simt.cu).
@@ -57,6 +62,9 @@ struct TcParams {
   const float* act_scale; const float* act_shift;   // optional affine before the activation of out_act
   uint32_t idesc;           // tcgen05 instruction descriptor
   uint32_t a_stage_bytes, b_stage_bytes;
+  uint32_t row_bytes;       // bytes of one K-chunk row: KC * element size (128, or 64 for bf16 KC = 32)
+  uint32_t at_bytes;        // TMA epilogue: bytes of one activated-operand staging tile (32 rows x 32 columns)
+  uint32_t at_double;       // ... double-buffered (bf16) or single (tf32: see the wait before it is rewritten)
   uint32_t sbo16;           // stride-byte-offset >> 4 of the K-major swizzled layout (8 rows)
   uint32_t layout_type;     // 2 = SWIZZLE_128B, 4 = SWIZZLE_64B
   uint32_t tmem_cols;
@@ -138,16 +146,14 @@ __device__ __forceinline__ uint32_t desc_lo(uint32_t saddr) { return ((saddr >> 
 __device__ __forceinline__ uint32_t desc_hi(uint32_t sbo16, uint32_t layout_type) {
   return (sbo16 & 0x3FFFu) | (1u << 14) | ((layout_type & 7u) << 29);
 }
-template <bool ACCUM>
+#define VFX_TC_MMA_ASM(SETP, KIND)                                                                                              \
+  asm volatile("{\n\t.reg .b64 da, db;\n\t.reg .pred p;\n\t" SETP " p, 0, 0;\n\tmov.b64 da, {%1, %3};\n\tmov.b64 db, {%2, %3};\n\t" \
+               "tcgen05.mma.cta_group::1.kind::" KIND " [%0], da, db, %4, p;\n\t}"                                               \
+               ::"r"(d_tmem), "r"(a_lo), "r"(b_lo), "r"(hi), "r"(idesc) : "memory")
+template <bool ACCUM, bool TF32>
 __device__ __forceinline__ void tc_mma_lo(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t hi, uint32_t idesc) {
-  if (ACCUM)
-    asm volatile("{\n\t.reg .b64 da, db;\n\t.reg .pred p;\n\tsetp.eq.b32 p, 0, 0;\n\tmov.b64 da, {%1, %3};\n\tmov.b64 db, {%2, %3};\n\t"
-                 "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n\t}"
-                 ::"r"(d_tmem), "r"(a_lo), "r"(b_lo), "r"(hi), "r"(idesc) : "memory");
-  else
-    asm volatile("{\n\t.reg .b64 da, db;\n\t.reg .pred p;\n\tsetp.ne.b32 p, 0, 0;\n\tmov.b64 da, {%1, %3};\n\tmov.b64 db, {%2, %3};\n\t"
-                 "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n\t}"
-                 ::"r"(d_tmem), "r"(a_lo), "r"(b_lo), "r"(hi), "r"(idesc) : "memory");
+  if (TF32) { if (ACCUM) VFX_TC_MMA_ASM("setp.eq.b32", "tf32"); else VFX_TC_MMA_ASM("setp.ne.b32", "tf32"); }
+  else      { if (ACCUM) VFX_TC_MMA_ASM("setp.eq.b32", "f16");  else VFX_TC_MMA_ASM("setp.ne.b32", "f16"); }
 }
 __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t* v) {
   asm volatile(
@@ -210,7 +216,7 @@ struct TileIter {
   }
 };
 
-template <int ACT>
+template <int ACT, bool TF32>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
                     const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CUtensorMap tmO,
@@ -256,7 +262,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       ash_s[i] = p.act_scale ? p.act_shift[i] : 0.f;
     }
   if (p.halo) {   // rows behind the TMA box (read by the last taps' views, never written by TMA) must be zero
-    const uint32_t row_b = (uint32_t)(p.KC * 2), used = p.halo_rows * row_b, blk = p.halo_kc_bytes;
+    const uint32_t row_b = p.row_bytes, used = p.halo_rows * row_b, blk = p.halo_kc_bytes;
     const uint32_t nblk = (uint32_t)p.stages * (uint32_t)p.n_kc, padw = (blk - used) / 4;
     if (padw)
       for (uint32_t i = threadIdx.x; i < nblk * padw; i += NUM_THREADS)
@@ -297,7 +303,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           mbar_wait_t(&empty[s], ph ^ 1, w_empty, dbg);
           uint8_t* sa = smem + (size_t)s * stage_bytes;
           if (elect_one()) {
-            mbar_expect_tx(&full[s], p.halo_rows * (uint32_t)(p.KC * 2) * (uint32_t)p.n_kc * p.halo_boxes);
+            mbar_expect_tx(&full[s], p.halo_rows * p.row_bytes * (uint32_t)p.n_kc * p.halo_boxes);
 #pragma unroll 1
             for (int kc = 0; kc < p.n_kc; ++kc) {
               if (p.halo_boxes == 1) {
@@ -305,7 +311,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
               } else {      // one aligned 128-row box per tap, all on this stage's barrier
 #pragma unroll 1
                 for (int tap = 0; tap < p.ntaps; ++tap)
-                  tma_load_4d(&tmA, &full[s], sa + (size_t)kc * p.halo_kc_bytes + (size_t)p.halo_off[tap] * (p.KC * 2), kc * p.KC,
+                  tma_load_4d(&tmA, &full[s], sa + (size_t)kc * p.halo_kc_bytes + (size_t)p.halo_off[tap] * p.row_bytes, kc * p.KC,
                               t.w0 + p.dw[tap], t.h0 + p.dh[tap], t.b);
               }
             }
@@ -350,7 +356,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     // ===================== MMA issuer (warp-uniform loop, one elected lane issues) =====================
     {
       uint32_t s = 0, ph = 0;
-      const int kk = p.KC / 16;                       // UMMA_K = 16 for bf16
+      const int kk = (int)(p.row_bytes / 32);         // MMAs per K chunk: UMMA_K = 16 bf16 / 8 tf32 elements = 32 bytes
       if (p.w_resident) { mbar_wait(wfull, 0); tc_fence_after(); }
       const bool dbg = p.dbg != nullptr;
       long long w_full = 0, w_te = 0, w_mma = 0, w_cm = 0, w_cm2 = 0; const long long tstart = dbg ? clock64() : 0;
@@ -377,24 +383,24 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 uint32_t a_lo[3], b_lo[3];
 #pragma unroll
                 for (int dt = 0; dt < 3; ++dt) {
-                  a_lo[dt] = desc_lo(s_addr + (uint32_t)kc * p.halo_kc_bytes + p.halo_off[tap0 + dt] * (uint32_t)(p.KC * 2));
+                  a_lo[dt] = desc_lo(s_addr + (uint32_t)kc * p.halo_kc_bytes + p.halo_off[tap0 + dt] * p.row_bytes);
                   b_lo[dt] = desc_lo(w_addr + (uint32_t)((tap0 + dt) * p.n_kc + kc) * p.b_stage_bytes);
                 }
-                if ((tap0 | kc) == 0) tc_mma_lo<false>(d_tmem, a_lo[0], b_lo[0], dhi, p.idesc);   // first MMA of the tile overwrites
-                else tc_mma_lo<true>(d_tmem, a_lo[0], b_lo[0], dhi, p.idesc);
+                if ((tap0 | kc) == 0) tc_mma_lo<false, TF32>(d_tmem, a_lo[0], b_lo[0], dhi, p.idesc);   // first MMA of the tile overwrites
+                else tc_mma_lo<true, TF32>(d_tmem, a_lo[0], b_lo[0], dhi, p.idesc);
                 if (kk == 4) {
 #pragma unroll
-                  for (int k = 1; k < 4; ++k) tc_mma_lo<true>(d_tmem, a_lo[0] + 2 * k, b_lo[0] + 2 * k, dhi, p.idesc);
+                  for (int k = 1; k < 4; ++k) tc_mma_lo<true, TF32>(d_tmem, a_lo[0] + 2 * k, b_lo[0] + 2 * k, dhi, p.idesc);
 #pragma unroll
                   for (int dt = 1; dt < 3; ++dt)
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) tc_mma_lo<true>(d_tmem, a_lo[dt] + 2 * k, b_lo[dt] + 2 * k, dhi, p.idesc);
+                    for (int k = 0; k < 4; ++k) tc_mma_lo<true, TF32>(d_tmem, a_lo[dt] + 2 * k, b_lo[dt] + 2 * k, dhi, p.idesc);
                 } else {
-                  tc_mma_lo<true>(d_tmem, a_lo[0] + 2, b_lo[0] + 2, dhi, p.idesc);
+                  tc_mma_lo<true, TF32>(d_tmem, a_lo[0] + 2, b_lo[0] + 2, dhi, p.idesc);
 #pragma unroll
                   for (int dt = 1; dt < 3; ++dt)
 #pragma unroll
-                    for (int k = 0; k < 2; ++k) tc_mma_lo<true>(d_tmem, a_lo[dt] + 2 * k, b_lo[dt] + 2 * k, dhi, p.idesc);
+                    for (int k = 0; k < 2; ++k) tc_mma_lo<true, TF32>(d_tmem, a_lo[dt] + 2 * k, b_lo[dt] + 2 * k, dhi, p.idesc);
                 }
               }
             }
@@ -424,12 +430,12 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             const long long tm0 = dbg ? clock64() : 0;
             if (elect_one()) {
               const uint32_t ghi = desc_hi(p.sbo16, p.layout_type), ga = desc_lo(a_addr), gb = desc_lo(b_addr);
-              if (ks == 0) tc_mma_lo<false>(d_tmem, ga, gb, ghi, p.idesc);
-              else tc_mma_lo<true>(d_tmem, ga, gb, ghi, p.idesc);
-              tc_mma_lo<true>(d_tmem, ga + 2, gb + 2, ghi, p.idesc);
+              if (ks == 0) tc_mma_lo<false, TF32>(d_tmem, ga, gb, ghi, p.idesc);
+              else tc_mma_lo<true, TF32>(d_tmem, ga, gb, ghi, p.idesc);
+              tc_mma_lo<true, TF32>(d_tmem, ga + 2, gb + 2, ghi, p.idesc);
               if (kk == 4) {
-                tc_mma_lo<true>(d_tmem, ga + 4, gb + 4, ghi, p.idesc);
-                tc_mma_lo<true>(d_tmem, ga + 6, gb + 6, ghi, p.idesc);
+                tc_mma_lo<true, TF32>(d_tmem, ga + 4, gb + 4, ghi, p.idesc);
+                tc_mma_lo<true, TF32>(d_tmem, ga + 6, gb + 6, ghi, p.idesc);
               }
               tc_commit(&empty[s]);                   // frees the smem stage when these MMAs retire
               if (ks == k_steps - 1) tc_commit(&tmem_full[(i0 + j) & nacc_mask]);   // accumulator ready for the epilogue
@@ -509,7 +515,11 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             *reinterpret_cast<float4*>(ro + ((uint32_t)(j << 4) ^ sw128)) = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
         }
         if (p.out_act) {
-          uint8_t* const at = at_base + k * 2048 + lane * 64;
+          uint8_t* const at_tile = at_base + (p.at_double ? k * p.at_bytes : 0u);
+          if (!p.at_double) {     // single staging tile: the store that read it (issued one chunk ago) must have drained
+            if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            __syncwarp();
+          }
           if (p.act_scale) {                          // fused eval-mode BatchNorm of the consumer
             const float4* sp = reinterpret_cast<const float4*>(asc_s + bcol - 64);
             const float4* tp = reinterpret_cast<const float4*>(ash_s + bcol - 64);
@@ -520,17 +530,27 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
               f[4 * j + 2] = fmaf(f[4 * j + 2], s4.z, t4.z); f[4 * j + 3] = fmaf(f[4 * j + 3], s4.w, t4.w);
             }
           }
+          if (TF32) {             // fp32 storage, values rounded to tf32: a SWIZZLE_128B tile like the raw one
+            uint8_t* const at = at_tile + lane * 128;
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            uint32_t w[4];
+            for (int j = 0; j < 8; ++j)
+              *reinterpret_cast<float4*>(at + ((uint32_t)(j << 4) ^ sw128)) =
+                  make_float4(round_tf32(act_fast<ACT>(f[4 * j], p.act_param)), round_tf32(act_fast<ACT>(f[4 * j + 1], p.act_param)),
+                              round_tf32(act_fast<ACT>(f[4 * j + 2], p.act_param)), round_tf32(act_fast<ACT>(f[4 * j + 3], p.act_param)));
+          } else {
+            uint8_t* const at = at_tile + lane * 64;
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              const float lo = act_fast<ACT>(f[8 * j + 2 * q], p.act_param);
-              const float hi = act_fast<ACT>(f[8 * j + 2 * q + 1], p.act_param);
-              __nv_bfloat162 h2 = __floats2bfloat162_rn(lo, hi);
-              w[q] = *reinterpret_cast<uint32_t*>(&h2);
+            for (int j = 0; j < 4; ++j) {
+              uint32_t w[4];
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                const float lo = act_fast<ACT>(f[8 * j + 2 * q], p.act_param);
+                const float hi = act_fast<ACT>(f[8 * j + 2 * q + 1], p.act_param);
+                __nv_bfloat162 h2 = __floats2bfloat162_rn(lo, hi);
+                w[q] = *reinterpret_cast<uint32_t*>(&h2);
+              }
+              *reinterpret_cast<uint4*>(at + ((uint32_t)(j << 4) ^ sw64)) = make_uint4(w[0], w[1], w[2], w[3]);
             }
-            *reinterpret_cast<uint4*>(at + ((uint32_t)(j << 4) ^ sw64)) = make_uint4(w[0], w[1], w[2], w[3]);
           }
         }
         const long long tq1 = dbg ? clock64() : 0;
@@ -540,7 +560,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         if (dbg) { w_math += tq1 - tq0; w_fence += tq2 - tq1; }
         if (lane == 0) {
           if (p.out_raw) tma_store_4d(&tmO, stg + k * 4096, p.o_col + col, t.w0 + dw0, t.h0 + dh0, t.b);
-          if (p.out_act) tma_store_4d(&tmT, at_base + k * 2048, p.oa_col + col, t.w0 + dw0, t.h0 + dh0, t.b);
+          if (p.out_act) tma_store_4d(&tmT, at_base + (p.at_double ? k * p.at_bytes : 0u), p.oa_col + col, t.w0 + dw0, t.h0 + dh0, t.b);
           asm volatile("cp.async.bulk.commit_group;" ::: "memory");
           { const long long t0 = dbg ? clock64() : 0;
             asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");   // buffers k^1 are free again
@@ -646,18 +666,26 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 f[4 * j + 2] = fmaf(f[4 * j + 2], s4.z, t4.z); f[4 * j + 3] = fmaf(f[4 * j + 3], s4.w, t4.w);
               }
             }
-            uint4* ap = reinterpret_cast<uint4*>(p.out_act + off_a + c0);
+            if (TF32) {
+              float4* ap = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out_act) + off_a + c0);
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              uint32_t w[4];
+              for (int j = 0; j < 8; ++j)
+                ap[j] = make_float4(round_tf32(act_fast<ACT>(f[4 * j], p.act_param)), round_tf32(act_fast<ACT>(f[4 * j + 1], p.act_param)),
+                                    round_tf32(act_fast<ACT>(f[4 * j + 2], p.act_param)), round_tf32(act_fast<ACT>(f[4 * j + 3], p.act_param)));
+            } else {
+              uint4* ap = reinterpret_cast<uint4*>(p.out_act + off_a + c0);
 #pragma unroll
-              for (int q = 0; q < 4; ++q) {
-                const float lo = act_fast<ACT>(f[8 * j + 2 * q], p.act_param);
-                const float hi = act_fast<ACT>(f[8 * j + 2 * q + 1], p.act_param);
-                __nv_bfloat162 h2 = __floats2bfloat162_rn(lo, hi);
-                w[q] = *reinterpret_cast<uint32_t*>(&h2);
+              for (int j = 0; j < 4; ++j) {
+                uint32_t w[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                  const float lo = act_fast<ACT>(f[8 * j + 2 * q], p.act_param);
+                  const float hi = act_fast<ACT>(f[8 * j + 2 * q + 1], p.act_param);
+                  __nv_bfloat162 h2 = __floats2bfloat162_rn(lo, hi);
+                  w[q] = *reinterpret_cast<uint32_t*>(&h2);
+                }
+                ap[j] = make_uint4(w[0], w[1], w[2], w[3]);
               }
-              ap[j] = make_uint4(w[0], w[1], w[2], w[3]);
             }
           }
         }
@@ -701,19 +729,24 @@ int ilog2(int v) { int l = 0; while ((1 << l) < v) ++l; return l; }
 
 }  // namespace
 
-int conv_gemm_tc(const vfx_conv_desc& d, cudaStream_t st) {
+int conv_gemm_tc(int precision, const vfx_conv_desc& d, cudaStream_t st) {
   // ---- shapes this kernel covers; everything else returns UNSUPPORTED (caller uses the SIMT kernel)
+  if (precision != VFX_PREC_BF16 && precision != VFX_PREC_TF32) return VFX_ERR_UNSUPPORTED;
+  const bool tf32 = precision == VFX_PREC_TF32;
+  const int esz = tf32 ? 4 : 2;
   int KC = 0;
-  if (d.Cin % 64 == 0) KC = 64; else if (d.Cin == 32) KC = 32;
+  if (tf32) { if (d.Cin % 32 == 0) KC = 32; }
+  else if (d.Cin % 64 == 0) KC = 64; else if (d.Cin == 32) KC = 32;
   if (!KC) return VFX_ERR_UNSUPPORTED;
+  const int al = 16 / esz;                 // elements per 16 bytes (TMA stride granularity)
   int Ntile = 0;
   for (int c : {256, 128, 64, 32}) if (d.N % c == 0) { Ntile = c; break; }
   if (!Ntile) return VFX_ERR_UNSUPPORTED;
   if (d.ntaps < 1 || d.ntaps > 9) return VFX_ERR_UNSUPPORTED;
-  if (d.a_sW % 8 || d.a_sH % 8 || d.a_sB % 8 || ((uintptr_t)d.a & 15) || ((uintptr_t)d.w & 15)) return VFX_ERR_UNSUPPORTED;
+  if (d.a_sW % al || d.a_sH % al || d.a_sB % al || ((uintptr_t)d.a & 15) || ((uintptr_t)d.w & 15)) return VFX_ERR_UNSUPPORTED;
   // epilogue vector alignment
   if (d.out_raw && (d.o_sW % 4 || d.o_sH % 4 || d.o_sB % 4 || d.o_col % 4 || ((uintptr_t)d.out_raw & 15))) return VFX_ERR_UNSUPPORTED;
-  if (d.out_act && (d.oa_sW % 8 || d.oa_sH % 8 || d.oa_sB % 8 || d.oa_col % 8 || ((uintptr_t)d.out_act & 15))) return VFX_ERR_UNSUPPORTED;
+  if (d.out_act && (d.oa_sW % al || d.oa_sH % al || d.oa_sB % al || d.oa_col % al || ((uintptr_t)d.out_act & 15))) return VFX_ERR_UNSUPPORTED;
   if (d.residual && (d.r_sW % 4 || d.r_sH % 4 || d.r_sB % 4 || d.r_col % 4 || ((uintptr_t)d.residual & 15))) return VFX_ERR_UNSUPPORTED;
   if (d.bias && (d.bias_mod % 32 || ((uintptr_t)d.bias & 15))) return VFX_ERR_UNSUPPORTED;
   for (int t = 0; t < d.ntaps; ++t) if (d.w_off[t] % d.Cin) return VFX_ERR_UNSUPPORTED;
@@ -744,13 +777,16 @@ int conv_gemm_tc(const vfx_conv_desc& d, cudaStream_t st) {
   p.residual = d.residual; p.r_sB = d.r_sB; p.r_sH = d.r_sH; p.r_sW = d.r_sW; p.r_col = d.r_col;
   p.act = d.act; p.act_param = d.act_param;
   p.act_scale = d.out_act ? d.act_scale : nullptr; p.act_shift = d.out_act ? d.act_shift : nullptr;
-  // instruction descriptor: c=F32 [4,6)=1, a=BF16 [7,10)=1, b=BF16 [10,13)=1, K-major both, N>>3 [17,23), M>>4 [24,29)
-  p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(Ntile >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
-  const uint32_t row_bytes = KC * 2;
+  // instruction descriptor: c=F32 [4,6)=1, a/b format [7,10)/[10,13) = 1 (BF16) or 2 (TF32), K-major both,
+  // N>>3 [17,23), M>>4 [24,29)
+  const uint32_t fmt = tf32 ? 2u : 1u;
+  p.idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(Ntile >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
+  const uint32_t row_bytes = KC * esz;
+  p.row_bytes = row_bytes;
   p.a_stage_bytes = TILE_M * row_bytes;
   p.b_stage_bytes = Ntile * row_bytes;
   p.sbo16 = (8 * row_bytes) >> 4;
-  p.layout_type = KC == 64 ? 2u : 4u;
+  p.layout_type = row_bytes == 128 ? 2u : 4u;
   p.nacc = 512 / Ntile > 8 ? 8 : 512 / Ntile;        // Ntile 256 -> 2, 128 -> 4, <= 64 -> 8
   p.tmem_cols = 32;
   while (p.tmem_cols < p.nacc * Ntile) p.tmem_cols <<= 1;
@@ -767,7 +803,11 @@ int conv_gemm_tc(const vfx_conv_desc& d, cudaStream_t st) {
   p.epi_arrivals = 32u * NUM_EPI_WARPS;
   const bool needs_ro = d.out_raw || d.residual;
   p.epi_at_off = needs_ro ? 8192u : 0u;
-  p.epi_warp_bytes = p.epi_at_off + (d.out_act ? 4096u : 0u);
+  // activated-operand staging: bf16 2 x 2 KB (double-buffered); tf32 2 x 4 KB when it is the only output, one 4 KB tile
+  // next to the raw/residual tiles (8 warps x 16 KB would leave no room for the operand stages)
+  p.at_bytes = tf32 ? 4096u : 2048u;
+  p.at_double = (tf32 && needs_ro) ? 0u : 1u;
+  p.epi_warp_bytes = p.epi_at_off + (d.out_act ? p.at_bytes * (p.at_double ? 2u : 1u) : 0u);
   p.bias_floats = ((uint32_t)d.N + 63u) & ~63u;
   const uint32_t epi_smem = p.tma_epi ? NUM_EPI_WARPS * p.epi_warp_bytes + 3 * p.bias_floats * 4 : 0u;
   if (p.w_resident && p.w_bytes + epi_smem + 3 * p.a_stage_bytes > SMEM_BUDGET) { p.w_resident = 0; p.w_bytes = 0; }
@@ -777,10 +817,10 @@ int conv_gemm_tc(const vfx_conv_desc& d, cudaStream_t st) {
   p.halo = 0;
   uint32_t halo_box_w = 0, halo_box_h = 0;
   if (allow_halo && p.w_resident) {
-    const uint32_t row_b = (uint32_t)KC * 2;
+    const uint32_t row_b = row_bytes;
     bool ok = false;
     uint32_t box_w = 0, box_h = 0, extra = 0;
-    if (d.H == 1 && d.Hq == 1 && d.ntaps == 3 && tw == TILE_M && KC == 64 && d.dw[1] == 0 && d.dw[2] > 0 && d.dw[2] <= 64 &&
+    if (d.H == 1 && d.Hq == 1 && d.ntaps == 3 && tw == TILE_M && row_bytes == 128 && d.dw[1] == 0 && d.dw[2] > 0 && d.dw[2] <= 64 &&
         d.dw[0] == -d.dw[2] && d.dh[0] == 0 && d.dh[1] == 0 && d.dh[2] == 0) {
       const int dd = d.dw[2];
       box_w = TILE_M + 2 * dd; box_h = 1; p.halo_pw = dd; p.halo_ph = 0;
@@ -795,7 +835,7 @@ int conv_gemm_tc(const vfx_conv_desc& d, cudaStream_t st) {
       box_w = (uint32_t)tw; box_h = (uint32_t)th + 2; p.halo_pw = 1; p.halo_ph = 1; extra = 2;
     }
     p.halo_boxes = 1;
-    if (!ok && d.H == 1 && d.Hq == 1 && d.ntaps == 3 && tw == TILE_M && KC == 64) {
+    if (!ok && d.H == 1 && d.Hq == 1 && d.ntaps == 3 && tw == TILE_M && row_bytes == 128) {
       // large dilation: the taps' boxes do not overlap -> one aligned 128-row box per tap, but still ONE pipeline
       // stage / barrier round trip per tile
       box_w = TILE_M; box_h = 1; p.halo_pw = 0; p.halo_ph = 0; p.halo_boxes = 3;
@@ -822,24 +862,25 @@ int conv_gemm_tc(const vfx_conv_desc& d, cudaStream_t st) {
 
   // ---- tensor maps
   CUtensorMap tmA, tmW;
-  const CUtensorMapSwizzle swz = KC == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+  const CUtensorMapSwizzle swz = row_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+  const CUtensorMapDataType op_dt = tf32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
   {
     cuuint64_t dims[4] = {(cuuint64_t)d.Cin, (cuuint64_t)d.W, (cuuint64_t)d.H, (cuuint64_t)d.B};
-    cuuint64_t strides[3] = {(cuuint64_t)d.a_sW * 2, (cuuint64_t)d.a_sH * 2, (cuuint64_t)d.a_sB * 2};
+    cuuint64_t strides[3] = {(cuuint64_t)d.a_sW * esz, (cuuint64_t)d.a_sH * esz, (cuuint64_t)d.a_sB * esz};
     // a degenerate dimension of extent 1 may carry any stride; keep them valid multiples of 16
     cuuint32_t box[4] = {(cuuint32_t)KC, (cuuint32_t)(p.halo ? halo_box_w : (uint32_t)tw), (cuuint32_t)(p.halo ? halo_box_h : (uint32_t)th), 1};
     cuuint32_t estr[4] = {1, 1, 1, 1};
-    CUresult r = encode(&tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(d.a), dims, strides, box, estr,
+    CUresult r = encode(&tmA, op_dt, 4, const_cast<void*>(d.a), dims, strides, box, estr,
                         CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error("conv_gemm_tc: cuTensorMapEncodeTiled(A) failed with %d", (int)r); return VFX_ERR_CUDA; }
   }
   {
     cuuint64_t dims[2] = {(cuuint64_t)d.Cin, (cuuint64_t)max_row};
-    cuuint64_t strides[1] = {(cuuint64_t)d.Cin * 2};
+    cuuint64_t strides[1] = {(cuuint64_t)d.Cin * esz};
     cuuint32_t box[2] = {(cuuint32_t)KC, (cuuint32_t)Ntile};
     cuuint32_t estr[2] = {1, 1};
-    CUresult r = encode(&tmW, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(d.w), dims, strides, box, estr,
+    CUresult r = encode(&tmW, op_dt, 2, const_cast<void*>(d.w), dims, strides, box, estr,
                         CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error("conv_gemm_tc: cuTensorMapEncodeTiled(W) failed with %d", (int)r); return VFX_ERR_CUDA; }
@@ -860,7 +901,9 @@ int conv_gemm_tc(const vfx_conv_desc& d, cudaStream_t st) {
     CUresult r = CUDA_SUCCESS;
     if (d.residual) r = enc(&tmR, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, d.residual, d.r_col + d.N, d.r_sW, d.r_sH, d.r_sB, CU_TENSOR_MAP_SWIZZLE_128B);
     if (r == CUDA_SUCCESS && d.out_raw) r = enc(&tmO, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, d.out_raw, d.o_col + d.N, d.o_sW, d.o_sH, d.o_sB, CU_TENSOR_MAP_SWIZZLE_128B);
-    if (r == CUDA_SUCCESS && d.out_act) r = enc(&tmT, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, d.out_act, d.oa_col + d.N, d.oa_sW, d.oa_sH, d.oa_sB, CU_TENSOR_MAP_SWIZZLE_64B);
+    if (r == CUDA_SUCCESS && d.out_act)
+      r = tf32 ? enc(&tmT, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, d.out_act, d.oa_col + d.N, d.oa_sW, d.oa_sH, d.oa_sB, CU_TENSOR_MAP_SWIZZLE_128B)
+               : enc(&tmT, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, d.out_act, d.oa_col + d.N, d.oa_sW, d.oa_sH, d.oa_sB, CU_TENSOR_MAP_SWIZZLE_64B);
     if (r != CUDA_SUCCESS) { set_error("conv_gemm_tc: cuTensorMapEncodeTiled(epilogue) failed with %d", (int)r); return VFX_ERR_CUDA; }
   }
 
@@ -875,7 +918,9 @@ int conv_gemm_tc(const vfx_conv_desc& d, cudaStream_t st) {
     int dev = 0;
     VFX_CUDA_CHECK(cudaGetDevice(&dev));
     VFX_CUDA_CHECK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
-#define VFX_TC_ATTR(A) VFX_CUDA_CHECK(cudaFuncSetAttribute(conv_gemm_tc_kernel<A>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024))
+#define VFX_TC_ATTR(A)                                                                                                              \
+  VFX_CUDA_CHECK(cudaFuncSetAttribute(conv_gemm_tc_kernel<A, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); \
+  VFX_CUDA_CHECK(cudaFuncSetAttribute(conv_gemm_tc_kernel<A, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024))
     VFX_TC_ATTR(VFX_ACT_NONE); VFX_TC_ATTR(VFX_ACT_LRELU); VFX_TC_ATTR(VFX_ACT_ELU); VFX_TC_ATTR(VFX_ACT_LRELU_XSINX);
     VFX_TC_ATTR(VFX_ACT_SIGMOID);
 #undef VFX_TC_ATTR
@@ -890,7 +935,11 @@ int conv_gemm_tc(const vfx_conv_desc& d, cudaStream_t st) {
   }
   const int act = d.out_act ? d.act : VFX_ACT_NONE;
   switch (act) {
-#define VFX_TC_LAUNCH(A) case A: conv_gemm_tc_kernel<A><<<grid, NUM_THREADS, smem_bytes, st>>>(tmA, tmW, tmR, tmO, tmT, p); break
+#define VFX_TC_LAUNCH(A)                                                                                       \
+  case A:                                                                                                      \
+    if (tf32) conv_gemm_tc_kernel<A, true><<<grid, NUM_THREADS, smem_bytes, st>>>(tmA, tmW, tmR, tmO, tmT, p);  \
+    else conv_gemm_tc_kernel<A, false><<<grid, NUM_THREADS, smem_bytes, st>>>(tmA, tmW, tmR, tmO, tmT, p);      \
+    break
     VFX_TC_LAUNCH(VFX_ACT_NONE); VFX_TC_LAUNCH(VFX_ACT_LRELU); VFX_TC_LAUNCH(VFX_ACT_ELU);
     VFX_TC_LAUNCH(VFX_ACT_LRELU_XSINX); VFX_TC_LAUNCH(VFX_ACT_SIGMOID);
 #undef VFX_TC_LAUNCH

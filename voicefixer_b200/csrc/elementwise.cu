@@ -295,6 +295,8 @@ int bn_act(int precision, const float* x, long long x_sB, long long ldx, int B, 
                           reinterpret_cast<T*>(y), y_sB, ldy)
   if (precision == VFX_PREC_BF16) {
     if (vec) VFX_BN_LAUNCH(bn_act_kernel, __nv_bfloat16); else VFX_BN_LAUNCH(bn_act_scalar_kernel, __nv_bfloat16);
+  } else if (precision == VFX_PREC_TF32) {
+    if (vec) VFX_BN_LAUNCH(bn_act_kernel, tf32_t); else VFX_BN_LAUNCH(bn_act_scalar_kernel, tf32_t);
   } else {
     if (vec) VFX_BN_LAUNCH(bn_act_kernel, float); else VFX_BN_LAUNCH(bn_act_scalar_kernel, float);
   }
@@ -352,6 +354,8 @@ int voc_normalize(const float* mel, int B, int T, int Tc, int input_is_log, cons
   if (precision == VFX_PREC_BF16)
     voc_normalize_kernel<__nv_bfloat16><<<g, 256, 0, st>>>(mel, B, T, Tc, input_is_log, tab,
                                                            reinterpret_cast<__nv_bfloat16*>(cond));
+  else if (precision == VFX_PREC_TF32)
+    voc_normalize_kernel<tf32_t><<<g, 256, 0, st>>>(mel, B, T, Tc, input_is_log, tab, reinterpret_cast<tf32_t*>(cond));
   else
     voc_normalize_kernel<float><<<g, 256, 0, st>>>(mel, B, T, Tc, input_is_log, tab,
                                                    reinterpret_cast<float*>(cond));
@@ -362,6 +366,8 @@ int voc_normalize(const float* mel, int B, int T, int Tc, int input_is_log, cons
 int cast_rows(const float* x, long long n, void* y, int precision, cudaStream_t st) {
   if (precision == VFX_PREC_BF16)
     cast_kernel<__nv_bfloat16><<<grid_for(n), 256, 0, st>>>(x, n, reinterpret_cast<__nv_bfloat16*>(y));
+  else if (precision == VFX_PREC_TF32)
+    cast_kernel<tf32_t><<<grid_for(n), 256, 0, st>>>(x, n, reinterpret_cast<tf32_t*>(y));
   else
     cast_kernel<float><<<grid_for(n), 256, 0, st>>>(x, n, reinterpret_cast<float*>(y));
   VFX_LAUNCH_CHECK();

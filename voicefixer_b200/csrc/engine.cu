@@ -35,7 +35,7 @@ struct vfx_engine {
   int device = 0;   // -1: planning-only engine (no CUDA calls; finalize and workspace queries only)
   int precision = VFX_PREC_FP32;
   bool finalized = false;
-  int use_tc = 1;   // BF16: tcgen05 kernel where the shape allows (0 = SIMT bf16 cross-check)
+  int use_tc = 1;   // BF16 / TF32: tcgen05 kernel where the shape allows (0 = SIMT cross-check on the same operands)
   std::unordered_map<std::string, vfx::Tensor> tensors;
   float* d_window = nullptr;    // periodic Hann, 2048
   float2* d_tw = nullptr;       // exp(-2 pi i k / 2048), k < 1024
@@ -44,7 +44,8 @@ struct vfx_engine {
   int profile = 0;
   std::vector<vfx::ProfRec> prof;
   std::string prof_report;
-  size_t esz() const { return precision == VFX_PREC_BF16 ? 2 : 4; }
+  size_t esz() const { return vfx::prec_esz(precision); }
+  bool tensor_core() const { return precision != VFX_PREC_FP32; }   // operands are a tensor-core format (bf16 / tf32)
 };
 
 namespace vfx {
@@ -99,7 +100,7 @@ double conv_flops(const vfx_conv_desc& d) {
 // algorithmic HBM bytes of one conv launch: the input tensor once (taps re-read from L2), fp32 residual in,
 // fp32 raw out, operand out (weights are negligible and stay in L2)
 double conv_bytes(const vfx_conv_desc& d, int prec) {
-  const double esz = prec == VFX_PREC_BF16 ? 2.0 : 4.0;
+  const double esz = (double)prec_esz(prec);
   const double M = (double)d.B * d.Hq * d.Wq;
   return (double)d.B * d.H * d.W * d.Cin * esz + M * d.N * ((d.residual ? 4.0 : 0.0) + (d.out_raw ? 4.0 : 0.0) + (d.out_act ? esz : 0.0));
 }
@@ -123,15 +124,15 @@ const void* get(Ctx& c, const std::string& name, size_t bytes) {
 }
 const float* getf(Ctx& c, const std::string& name, size_t n) { return (const float*)get(c, name, n * 4); }
 const void* getw(Ctx& c, const std::string& name, size_t n, int prec) {
-  return get(c, name, n * (prec == VFX_PREC_BF16 ? 2 : 4));
+  return get(c, name, n * prec_esz(prec));
 }
 
 int run_conv(Ctx& c, int prec, const vfx_conv_desc& d, const char* tag = "conv") {
   if (c.dry) return VFX_OK;
   if (c.rc != VFX_OK) return c.rc;
   ProfScope ps(c, tag, conv_flops(d), conv_bytes(d, prec));
-  if (prec == VFX_PREC_BF16 && c.e->use_tc) {
-    int r = conv_gemm_tc(d, c.st);
+  if (prec != VFX_PREC_FP32 && c.e->use_tc) {
+    int r = conv_gemm_tc(prec, d, c.st);
     if (r != VFX_ERR_UNSUPPORTED) return r;
   }
   return conv_gemm_simt(prec, d, c.st);
@@ -194,7 +195,7 @@ int bn_act_op(Ctx& c, int prec, const std::string& bn, int bn_C, const float* x,
   BnRef r;
   VFX_TRY(bn_resolve(c, bn, bn_C, x, x_sB, ldx, B, P, C, &r));
   if (c.dry) return VFX_OK;
-  ProfScope ps(c, "bn_act", 0.0, (double)B * P * C * (4 + (prec == VFX_PREC_BF16 ? 2 : 4)));
+  ProfScope ps(c, "bn_act", 0.0, (double)B * P * C * (4 + prec_esz(prec)));
   return bn_act(prec, x, x_sB, ldx, B, P, C, r.scale, r.shift, bn_C, r.stat_sB, act, slope, y,
                 (long long)P * C, C, c.st);
 }
@@ -216,18 +217,18 @@ int conv_block(Ctx& c, const std::string& p, const float* in, long long ld_in, i
   const int prec = c.prec();
   const long long P = (long long)H * W;
   const bool fuse = !c.train();
-  // bf16 mode: a 2-channel input (first encoder block) is zero-padded to 32 operand channels so the block
+  // bf16 / tf32 modes: a 2-channel input (first encoder block) is zero-padded to 32 operand channels so the block
   // runs on the tensor-core kernel; the host packs conv1 / shortcut weights as [..][Cout][32] accordingly.
-  const int Cop = (prec == VFX_PREC_BF16 && Cin < 32) ? 32 : Cin;
+  const int Cop = (prec != VFX_PREC_FP32 && Cin < 32) ? 32 : Cin;
   if (Cop != Cin && !c.dry) {
-    VFX_CUDA_CHECK(cudaMemsetAsync(s.opA, 0, (size_t)B * P * Cop * 2, c.st));
-    VFX_CUDA_CHECK(cudaMemsetAsync(s.opX, 0, (size_t)B * P * Cop * 2, c.st));
+    VFX_CUDA_CHECK(cudaMemsetAsync(s.opA, 0, (size_t)B * P * Cop * prec_esz(prec), c.st));
+    VFX_CUDA_CHECK(cudaMemsetAsync(s.opX, 0, (size_t)B * P * Cop * prec_esz(prec), c.st));
   }
   if (!(fuse && fz.opA_ready)) {
     BnRef r;
     VFX_TRY(bn_resolve(c, p + ".bn1", Cin, in, P * ld_in, ld_in, B, P, Cin, &r));
     if (!c.dry) {
-      ProfScope ps(c, "bn_act", 0.0, (double)B * P * Cin * 6);
+      ProfScope ps(c, "bn_act", 0.0, (double)B * P * Cin * (4 + prec_esz(prec)));
       VFX_TRY(bn_act(prec, in, P * ld_in, ld_in, B, P, Cin, r.scale, r.shift, Cin, r.stat_sB, VFX_ACT_LRELU, 0.01f, s.opA,
                      P * Cop, Cop, c.st));
     }
@@ -398,7 +399,7 @@ int linear(Ctx& c, const void* a, long long M, int K, const std::string& p, int 
 // fp32 tensor -> dense GEMM operand: the tensor itself in fp32 mode, a bf16 copy in bf16 mode
 const void* dn_operand(Ctx& c, const float* x, long long M, int C, void* scratch, int* rc) {
   *rc = VFX_OK;
-  if (c.prec() == VFX_PREC_FP32) return x;
+  if (c.prec() == VFX_PREC_FP32) return x;      // bf16: a bf16 copy; tf32: a copy rounded to tf32
   if (!c.dry) *rc = bn_act(c.prec(), x, M * C, C, 1, M, C, nullptr, nullptr, 1, 0, VFX_ACT_NONE, 0.f, scratch, M * C, C, c.st);
   return scratch;
 }
@@ -657,7 +658,8 @@ int vfx_version(void) { return 100; }
 
 int vfx_engine_create(vfx_engine** out, int device, int precision) {
   VFX_REQUIRE(out != nullptr, "engine_create: out is null");
-  VFX_REQUIRE(precision == VFX_PREC_FP32 || precision == VFX_PREC_BF16, "engine_create: bad precision %d", precision);
+  VFX_REQUIRE(precision == VFX_PREC_FP32 || precision == VFX_PREC_BF16 || precision == VFX_PREC_TF32,
+              "engine_create: bad precision %d", precision);
   if (device == -1) {   // planning-only: weight-set validation and workspace sizing on a host without a GPU
     vfx_engine* e = new vfx_engine();
     e->device = -1; e->precision = precision;
@@ -905,8 +907,8 @@ int vfx_hf_cut(vfx_engine* e, const float* wav, int B, int L, float ratio, float
 int vfx_conv_gemm(int precision, int impl, const vfx_conv_desc* d, void* stream) {
   VFX_REQUIRE(d, "conv_gemm: null descriptor");
   if (impl == 1) {
-    VFX_REQUIRE(precision == VFX_PREC_BF16, "conv_gemm: tcgen05 implementation is bf16 only");
-    return conv_gemm_tc(*d, (cudaStream_t)stream);
+    VFX_REQUIRE(precision == VFX_PREC_BF16 || precision == VFX_PREC_TF32, "conv_gemm: the tcgen05 implementation takes bf16 or tf32 operands");
+    return conv_gemm_tc(precision, *d, (cudaStream_t)stream);
   }
   return conv_gemm_simt(precision, *d, (cudaStream_t)stream);
 }

@@ -43,6 +43,21 @@ template <> __device__ __forceinline__ float from_f<float>(float v) { return v; 
 template <> __device__ __forceinline__ __nv_bfloat16 from_f<__nv_bfloat16>(float v) {
   return __float2bfloat16_rn(v);
 }
+// VFX_PREC_TF32 operand element: fp32 storage holding a value already rounded to tf32 (10-bit mantissa,
+// round-to-nearest) by its producer, so that the tensor core's truncation of the low 13 bits is exact.
+// (Un-rounded operands make kind::tf32 truncate: a CPU simulation of the whole path gave 1.4e-2 waveform
+// rel-RMS with truncation against 1.7e-3 with round-to-nearest, tools/sim_precision.py.)
+struct tf32_t { float v; };
+__device__ __forceinline__ float round_tf32(float v) {
+  uint32_t u;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v));
+  return __uint_as_float(u);
+}
+__device__ __forceinline__ float to_f(tf32_t v) { return v.v; }
+template <> __device__ __forceinline__ tf32_t from_f<tf32_t>(float v) { return tf32_t{round_tf32(v)}; }
+
+// element size of a GEMM operand / weight in the given vfx_precision
+static inline size_t prec_esz(int precision) { return precision == VFX_PREC_BF16 ? 2 : 4; }
 
 __device__ __forceinline__ float apply_act(float v, int act, float p) {
   switch (act) {
@@ -59,7 +74,7 @@ __device__ __forceinline__ float apply_act(float v, int act, float p) {
 
 // ------------------------------------------------------------------ kernels (host launchers)
 int conv_gemm_simt(int precision, const vfx_conv_desc& d, cudaStream_t st);
-int conv_gemm_tc(const vfx_conv_desc& d, cudaStream_t st);   // tcgen05, bf16
+int conv_gemm_tc(int precision, const vfx_conv_desc& d, cudaStream_t st);   // tcgen05: bf16 (kind::f16) or tf32 (kind::tf32)
 
 // y = act(scale[b][c]*x + shift[b][c]); x fp32 [B][P][C] (row pitch ldx), y operand type.
 // bn_C == 1: single-channel BN (scale[b][0]).  stat_sB: element stride between items (0 = shared).
