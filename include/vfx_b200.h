@@ -157,6 +157,22 @@ enum vfx_act { VFX_ACT_NONE = 0, VFX_ACT_LRELU = 1, VFX_ACT_ELU = 2,
 /* impl: 0 = SIMT, 1 = tcgen05 (BF16 or TF32). */
 int vfx_conv_gemm(int precision, int impl, const vfx_conv_desc* d, void* stream);
 
+/* Fused ResStack pair (bf16 operands, tcgen05; C = 64 only, VFX_ERR_UNSUPPORTED otherwise):
+ *   x' = x + conv2_{k3,d=1}( lrelu_0.01( conv1_{k3,dilation}( a ) + b1 ) ) + b2,   a = lrelu_0.01(x) as bf16
+ * ResStack.forward voicefixer/vocoder/model/modules.py:592-595 (layers :550-576).  The intermediate never leaves the
+ * SM.  x [B][L][C] fp32 is read as the residual and, if write_raw, overwritten with x'; out_act (optional, bf16
+ * [B][L][C], must not alias a) receives act(x') for the next consumer.  w1 / w2: [3][C][C] bf16, tap-major. */
+typedef struct vfx_pair_desc {
+  const void* a;
+  float* x;
+  const void* w1; const float* b1; int dilation;
+  const void* w2; const float* b2;
+  int B, L, C;
+  int write_raw;
+  void* out_act; int act; float act_param;
+} vfx_pair_desc;
+int vfx_resstack_pair(const vfx_pair_desc* d, void* stream);
+
 /* One direction-pair GRU layer recurrence: gi[B][T][2][768] (x W_ih^T + b_ih, fwd|bwd),
  * whh_t[2][256][768] (W_hh transposed), bhh[2][768] -> out[B][T][512] (fwd 256 | bwd 256).
  * torch.nn.GRU gate order r,z,n (voicefixer/restorer/model.py:35-42,61). */

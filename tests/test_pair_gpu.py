@@ -1,0 +1,89 @@
+"""GPU tests of the fused ResStack pair kernel (vfx_resstack_pair: conv1 -> h on chip -> conv2 + residual, tcgen05)
+through the C ABI, against the same arithmetic spelled out with torch ops: bf16 operands (a, h, weights), fp32
+accumulation, fp32 residual stream.  Reference op: ResStack.forward voicefixer/vocoder/model/modules.py:592-595.
+
+Tolerances: fp32 output 1e-4 relative RMS (bf16 x bf16 products are exact in fp32; a rare bf16 rounding tie of the
+on-chip intermediate h may flip against torch's), activated bf16 output 4e-3 (one bf16 rounding)."""
+import ctypes
+import pytest
+import torch
+import torch.nn.functional as F
+from conftest import rel_rms
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _rnd(*shape, seed=0, scale=1.0):
+    g = torch.Generator().manual_seed(seed)
+    return (torch.randn(*shape, generator=g) * scale).to(DEV)
+
+
+def _pair(x, a, w1, b1, w2, b2, dil, write_raw=True, act="lrelu", act_param=0.01, want_act=True):
+    """x (B,L,C) fp32 [updated in place], a (B,L,C) bf16, w (C,C,3) bf16 torch layout."""
+    from voicefixer_b200 import _lib
+    lib = _lib.load()
+    B, L, C = x.shape
+    d = _lib.PairDesc()
+    w1p, w2p = w1.permute(2, 0, 1).contiguous(), w2.permute(2, 0, 1).contiguous()
+    out_act = torch.zeros(B, L, C, device=DEV, dtype=torch.bfloat16) if want_act else None
+    d.a, d.x = a.data_ptr(), x.data_ptr()
+    d.w1, d.b1, d.dilation, d.w2, d.b2 = w1p.data_ptr(), b1.data_ptr(), dil, w2p.data_ptr(), b2.data_ptr()
+    d.B, d.L, d.C, d.write_raw = B, L, C, int(write_raw)
+    d.out_act = out_act.data_ptr() if want_act else None
+    d.act, d.act_param = _lib.ACT[act], act_param
+    _lib.check(lib.vfx_resstack_pair(ctypes.byref(d), ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)),
+               "vfx_resstack_pair")
+    torch.cuda.synchronize()
+    return out_act
+
+
+def _ref(x, a, w1, b1, w2, b2, dil):
+    h = F.leaky_relu(F.conv1d(a.float().permute(0, 2, 1), w1.float(), b1, dilation=dil, padding=dil), 0.01)
+    h = h.bfloat16().float()
+    return x + F.conv1d(h, w2.float(), b2, padding=1).permute(0, 2, 1)
+
+
+@pytest.mark.parametrize("L,dil,B", [(1000, 1, 2), (5000, 3, 1), (300, 27, 2), (378, 9, 1), (4000, 81, 2),
+                                     (9000, 2187, 1), (125, 1, 1), (127, 729, 1), (20000, 243, 3)])
+def test_pair_matches_two_convolutions(L, dil, B):
+    torch.backends.cudnn.allow_tf32 = False
+    C = 64
+    x = _rnd(B, L, C, seed=1)
+    a = F.leaky_relu(x, 0.01).bfloat16()
+    w1, w2 = _rnd(C, C, 3, seed=2, scale=0.08).bfloat16(), _rnd(C, C, 3, seed=3, scale=0.08).bfloat16()
+    b1, b2 = _rnd(C, seed=4, scale=0.1), _rnd(C, seed=5, scale=0.1)
+    ref = _ref(x, a, w1, b1, w2, b2, dil)
+    xin = x.clone()
+    act = _pair(xin, a, w1, b1, w2, b2, dil)
+    assert rel_rms((xin - x).cpu(), (ref - x).cpu()) < 1e-4            # the update itself, not masked by the residual
+    assert rel_rms(act.float().cpu(), F.leaky_relu(ref, 0.01).cpu()) < 4e-3
+
+
+def test_pair_output_variants():
+    """operand-only output with the next up-sampler's activation (no raw write), and raw-only output (last pair)."""
+    torch.backends.cudnn.allow_tf32 = False
+    C, L, B, dil = 64, 3000, 2, 9
+    x = _rnd(B, L, C, seed=11)
+    a = F.leaky_relu(x, 0.01).bfloat16()
+    w1, w2 = _rnd(C, C, 3, seed=12, scale=0.08).bfloat16(), _rnd(C, C, 3, seed=13, scale=0.08).bfloat16()
+    b1, b2 = _rnd(C, seed=14, scale=0.1), _rnd(C, seed=15, scale=0.1)
+    ref = _ref(x, a, w1, b1, w2, b2, dil)
+    xin = x.clone()
+    act = _pair(xin, a, w1, b1, w2, b2, dil, write_raw=False, act="lrelu_xsinx", act_param=0.2)
+    assert torch.equal(xin, x)                                          # x untouched
+    u = F.leaky_relu(ref, 0.2)
+    assert rel_rms(act.float().cpu(), (u + torch.sin(u)).cpu()) < 4e-3
+    xin = x.clone()
+    assert _pair(xin, a, w1, b1, w2, b2, dil, want_act=False) is None
+    assert rel_rms((xin - x).cpu(), (ref - x).cpu()) < 1e-4
+
+
+def test_pair_rejects_other_widths():
+    from voicefixer_b200._lib import VfxError
+    x = _rnd(1, 200, 128, seed=21)
+    a = x.bfloat16()
+    w = _rnd(128, 128, 3, seed=22).bfloat16()
+    b = _rnd(128, seed=23)
+    with pytest.raises(VfxError, match="unsupported"):
+        _pair(x, a, w, b, w, b, 1)

@@ -47,6 +47,22 @@ def _worker(rank, world, port, ragged, q):
         ok = ok and out is not None and torch.equal(out, full * 2.0)
     else:
         ok = ok and out is None
+    # --- the per-step form: sizes exchanged once at construction, then exactly ONE collective per call
+    plan = parallel.WaveformGather(hi - lo, L, torch.float32, "cpu")
+    ok = ok and plan.total_items == n_items and plan.sizes == [parallel.shard_range(n_items, r, world)[1] -
+                                                             parallel.shard_range(n_items, r, world)[0] for r in range(world)]
+    calls = []
+    real_gather, real_all_gather = dist.gather, dist.all_gather
+    dist.gather = lambda *a, **k: (calls.append("gather"), real_gather(*a, **k))[1]
+    dist.all_gather = lambda *a, **k: (calls.append("all_gather"), real_all_gather(*a, **k))[1]
+    for step in range(3):
+        out = plan(full[lo:hi] * float(step + 1))
+        if rank == 0:
+            ok = ok and torch.equal(out, full * float(step + 1))
+        else:
+            ok = ok and out is None
+    dist.gather, dist.all_gather = real_gather, real_all_gather
+    ok = ok and calls == ["gather"] * 3
     q.put((rank, bool(ok)))
     dist.barrier()
     dist.destroy_process_group()

@@ -285,7 +285,7 @@ def test_api_modes_1_2_and_vocoder_oracle(tmp_path, monkeypatch, states):
     assert out1.shape == ref1.shape == (1, 512 * (wav.shape[0] // 512))
     # mode 1 tolerance 1e-3: the fp32 rFFT -> irFFT round trip of the pre-filter differs from numpy's by ~4e-5 on a
     # noisy input (cut bins identical), which the network amplifies ~6x; with the oracle's filtered input the
-    # restore matches to 4e-6 (tools/dbg_mode1.py)
+    # restore matches to 4e-6
     assert rel_rms(out1, ref1) < 1e-3
     # mode 2 (train-mode BN, no dropout masks): <= 64 frames is an error in the reference too (1x1 UNet centre)
     with pytest.raises(ValueError, match="more than 1 value per channel"):

@@ -32,6 +32,12 @@ class ConvDesc(ctypes.Structure):
     ]
 
 
+class PairDesc(ctypes.Structure):
+    """struct vfx_pair_desc (include/vfx_b200.h)."""
+    _fields_ = [("a", _vp), ("x", _vp), ("w1", _vp), ("b1", _vp), ("dilation", _i), ("w2", _vp), ("b2", _vp),
+                ("B", _i), ("L", _i), ("C", _i), ("write_raw", _i), ("out_act", _vp), ("act", _i), ("act_param", _f)]
+
+
 # name -> (restype, argtypes); must list every symbol include/vfx_b200.h declares
 SIGNATURES = {
     "vfx_last_error": (_c.c_char_p, []),
@@ -52,6 +58,7 @@ SIGNATURES = {
     "vfx_restore": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp, _sz, _vp]),
     "vfx_hf_cut": (_i, [_vp, _vp, _i, _i, _f, _vp, _vp, _vp, _sz, _vp]),
     "vfx_conv_gemm": (_i, [_i, _i, _c.POINTER(ConvDesc), _vp]),
+    "vfx_resstack_pair": (_i, [_c.POINTER(PairDesc), _vp]),
     "vfx_gru_layer": (_i, [_vp, _vp, _vp, _i, _i, _vp, _vp]),
 }
 

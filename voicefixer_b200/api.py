@@ -124,6 +124,17 @@ class VoiceFixer:
         self._vocoder = Vocoder(44100, _engine=self._engine)
         self._model = _ModelShim(self)
 
+    @classmethod
+    def from_engine(cls, engine):
+        """The same API object around an engine whose weights are already on the device (e.g. an arena received through
+        parallel.broadcast_arena on a non-zero rank: no checkpoint files are read)."""
+        self = cls.__new__(cls)
+        self.analysis_module_ckpt = os.path.join(os.path.expanduser("~"), ANALYSIS_CKPT)
+        self._engine = engine
+        self._vocoder = Vocoder(44100, _engine=engine)
+        self._model = _ModelShim(self)
+        return self
+
     # -- helpers kept from the reference API
     def _load_wav(self, path, sample_rate, threshold=0.95):
         return wavio.load_mono(path, sample_rate)                       # base.py:47-49
@@ -165,46 +176,109 @@ class VoiceFixer:
             bp += SEG_LENGTH
         eng = self._engine
         dev = f"cuda:{eng.device}"
-        res = []
         groups = {}
         for i, s in enumerate(segs):
             groups.setdefault(len(s), []).append(i)
         outs = [None] * len(segs)
-        for L, idxs in groups.items():
-            if mode == 2 and 1 + (512 * (L // 512) if mode == 1 else L) // 441 <= 64:
+        for L, all_idxs in groups.items():
+            Lnet = 512 * (L // 512) if mode == 1 else L                  # mode 1's pre-filter shortens the segment
+            if mode == 2 and 1 + Lnet // 441 <= 64:
                 # torch.nn.functional.batch_norm in the reference (train mode, 1x1 UNet centre)
                 raise ValueError("Expected more than 1 value per channel when training, got input size "
                                  "torch.Size([1, 384, 1, 1])")
-            x = torch.from_numpy(np.stack([segs[i] for i in idxs])).to(dev)
-            if mode == 1:
-                x, _ = eng.hf_cut(x)                                     # shorter: 512*(L//512)
-            masks = None
-            if mode == 2 and drop_masks_fn is not False:
-                T = 1 + x.shape[1] // 441
-                # the reference's mode 2 is module.train(): both Dropout(0.5) of the denoiser are live and draw
-                # from torch's global RNG (base.py:114-115, restorer/model.py:76,90).  Same distribution here
-                # (keep-masks from torch's CPU generator, so torch.manual_seed controls it); the RNG *stream*
-                # differs from the reference's, which no reference test pins.  drop_masks_fn=False disables it.
-                masks = drop_masks_fn(x.shape[0], T) if drop_masks_fn else (torch.rand(2, x.shape[0], T, 512) >= 0.5)
-                masks = torch.as_tensor(masks).to(torch.uint8)
-                if tuple(masks.shape) != (2, x.shape[0], T, 512):
-                    raise ValueError(f"dropout masks must have shape (2, {x.shape[0]}, {T}, 512), got {tuple(masks.shape)}")
-            if your_vocoder_func is None:
-                y = eng.restore(x, mode=2 if mode == 2 else 0, drop_masks=masks)
-            else:                                                        # base.py:126-129
-                mel = eng.frontend(x)
-                mel_log = eng.analysis(mel, mode=2 if mode == 2 else 0, drop_masks=masks)
-                denoised = (10 ** torch.clip(mel_log, max=5))[:, None]
-                y = your_vocoder_func(denoised)
-                y = torch.as_tensor(y).to(dev).float()
-                if torch.max(torch.abs(y)) > 1.0:                        # base.py:131-133
-                    y = y / torch.max(torch.abs(y))
-                    print("Warning: Exceed energy limit,", "input")
-                y, _ = self._trim_center(y[:, 0], x)
-            for k, i in enumerate(idxs):
-                outs[i] = y[k]
+            # the reference walks the segments one at a time in constant memory; here they are batched, in chunks
+            # sized to the device memory that is free right now (a 100-minute recording does not fit one launch sequence)
+            chunk = eng.max_batch(L)
+            for c0 in range(0, len(all_idxs), chunk):
+                idxs = all_idxs[c0:c0 + chunk]
+                x = torch.from_numpy(np.stack([segs[i] for i in idxs])).to(dev)
+                if mode == 1:
+                    x, _ = eng.hf_cut(x)                                 # shorter: 512*(L//512)
+                masks = None
+                if mode == 2 and drop_masks_fn is not False:
+                    T = 1 + x.shape[1] // 441
+                    # the reference's mode 2 is module.train(): both Dropout(0.5) of the denoiser are live and draw
+                    # from torch's global RNG (base.py:114-115, restorer/model.py:76,90).  Same distribution here
+                    # (keep-masks from torch's CPU generator, so torch.manual_seed controls it); the RNG *stream*
+                    # differs from the reference's, which no reference test pins.  drop_masks_fn=False disables it.
+                    masks = drop_masks_fn(x.shape[0], T) if drop_masks_fn else (torch.rand(2, x.shape[0], T, 512) >= 0.5)
+                    masks = torch.as_tensor(masks).to(torch.uint8)
+                    if tuple(masks.shape) != (2, x.shape[0], T, 512):
+                        raise ValueError(f"dropout masks must have shape (2, {x.shape[0]}, {T}, 512), got {tuple(masks.shape)}")
+                if your_vocoder_func is None:
+                    y = eng.restore(x, mode=2 if mode == 2 else 0, drop_masks=masks)
+                else:                                                    # base.py:126-129
+                    mel = eng.frontend(x)
+                    mel_log = eng.analysis(mel, mode=2 if mode == 2 else 0, drop_masks=masks)
+                    denoised = (10 ** torch.clip(mel_log, max=5))[:, None]
+                    ys = []
+                    for k in range(denoised.shape[0]):                   # the hook sees what the reference hands it:
+                        m = denoised[k:k + 1]                            # one segment [1, 1, T, 128], on the CPU unless cuda
+                        yk = torch.as_tensor(your_vocoder_func(m if cuda else m.cpu())).to(dev).float()
+                        if torch.max(torch.abs(yk)) > 1.0:               # base.py:131-133, per segment
+                            yk = yk / torch.max(torch.abs(yk))
+                            print("Warning: Exceed energy limit,", "input")
+                        ys.append(self._trim_center(yk[:, 0], x[k:k + 1])[0])
+                    y = torch.cat(ys, 0)
+                for k, i in enumerate(idxs):
+                    outs[i] = y[k]
         out = torch.cat(outs, -1)[None]
         return out.cpu().numpy()
+
+    # ------------------------------------------------------------------ batch entry point (extension)
+    def pinned_empty(self, shape):
+        """numpy float32 array backed by pinned (page-locked) host memory: restore_batch copies such arrays to and from
+        the GPU without an extra staging copy."""
+        t = torch.empty(tuple(shape), dtype=torch.float32).pin_memory()
+        a = t.numpy()
+        self._pinned_keep = getattr(self, "_pinned_keep", [])
+        self._pinned_keep.append(t)
+        return a
+
+    @torch.no_grad()
+    def restore_batch(self, wavs, cuda=True, mode=0, out=None):
+        """Extension of the reference API for many utterances of one length (the reference restores one array per call,
+        voicefixer/base.py:106): wavs np (B, L) float32, L <= 30 s -> np (B, L) float32, every row exactly what
+        restore_inmem(row, mode) returns (mode 0 here; modes 1 / 2 go through restore_inmem).  The launch sequence of a
+        shape is captured into a CUDA graph on first use and replayed afterwards; host buffers move through pinned
+        staging (directly, when `wavs` / `out` are pinned: see pinned_empty).  Without `out`, the result is a view of an
+        internal pinned buffer that the next call with the same shape overwrites."""
+        _check_cuda(cuda)
+        if mode != 0:
+            raise ValueError("restore_batch runs mode 0; use restore_inmem for modes 1 and 2")
+        x = np.ascontiguousarray(wavs, dtype=np.float32)
+        if x.ndim != 2 or x.shape[1] > SEG_LENGTH:
+            raise ValueError("restore_batch takes (B, L) with L <= 30 s (longer inputs: restore_inmem segments them)")
+        eng = self._engine
+        dev = f"cuda:{eng.device}"
+        plans = self.__dict__.setdefault("_batch_plans", {})
+        key = tuple(x.shape)
+        if key not in plans:
+            if len(plans) >= 4:                                            # a few shapes at most: graphs own workspaces
+                plans.pop(next(iter(plans)))
+            p = {"dev_in": torch.empty(key, device=dev), "dev_out": torch.empty(key, device=dev),
+                 "host_in": torch.empty(key).pin_memory(), "host_out": torch.empty(key).pin_memory()}
+            p["dev_in"].copy_(torch.from_numpy(x))
+            p["graph"] = eng.make_graph(p["dev_in"], p["dev_out"], mode=0)
+            plans[key] = p
+        p = plans[key]
+        src = torch.from_numpy(x)
+        if not src.is_pinned():
+            p["host_in"].copy_(src)
+            src = p["host_in"]
+        p["dev_in"].copy_(src, non_blocking=True)
+        p["graph"].replay()
+        dst = p["host_out"]
+        if out is not None:
+            o = torch.from_numpy(out)
+            if o.is_pinned() and o.is_contiguous() and tuple(o.shape) == key and o.dtype == torch.float32:
+                dst = o
+        dst.copy_(p["dev_out"], non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        if out is not None and dst is p["host_out"]:
+            out[...] = dst.numpy()
+            return out
+        return out if out is not None else dst.numpy()
 
     def restore(self, input, output, cuda=False, mode=0, your_vocoder_func=None):
         wav_10k = self._load_wav(input, sample_rate=44100)               # base.py:141-146

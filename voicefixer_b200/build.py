@@ -7,7 +7,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libvfx_b200.so")
-SOURCES = ["engine.cu", "conv_gemm_simt.cu", "conv_gemm_tc.cu", "elementwise.cu", "frontend.cu",
+SOURCES = ["engine.cu", "conv_gemm_simt.cu", "conv_gemm_tc.cu", "resstack_pair_tc.cu", "elementwise.cu", "frontend.cu",
            "gru.cu", "hf_cut.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
@@ -58,6 +58,7 @@ def build(force=False, verbose=False):
         src = os.path.join(CSRC, s)
         if (not force and os.path.exists(obj) and os.path.getmtime(obj) > os.path.getmtime(src)
                 and os.path.getmtime(obj) > os.path.getmtime(os.path.join(CSRC, "vfx_common.cuh"))
+                and os.path.getmtime(obj) > os.path.getmtime(os.path.join(CSRC, "tc_ptx.cuh"))
                 and os.path.getmtime(obj) > os.path.getmtime(os.path.join(HERE, "..", "include", "vfx_b200.h"))):
             continue
         cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj]

@@ -41,6 +41,7 @@ struct vfx_engine {
   float2* d_tw = nullptr;       // exp(-2 pi i k / 2048), k < 1024
   std::vector<std::string> missing;
   int parts = 0;    // VFX_PART_* bits of the weight sets found complete by vfx_engine_finalize
+  int fuse_pair = 1;  // BF16: ResStack pairs of width 64 run as ONE fused kernel (resstack_pair_tc.cu)
   int profile = 0;
   std::vector<vfx::ProfRec> prof;
   std::string prof_report;
@@ -569,10 +570,36 @@ int vocoder_generator(Ctx& c, const void* cond, int B, int Tc, float* wav_out, i
       }
     }
     // ---- ResStack: 8 x (x + conv_k3_d1(lrelu(conv_k3_d3^i(lrelu(x))))), modules.py:550-576,592-595
+    // bf16, width 64: each pair is ONE fused kernel (h stays on chip); the activated operand copy ping-pongs between
+    // A0 and Hh because a pair reads it with a halo that neighbouring tiles would overwrite in place.
+    const bool fuse_pairs = prec == VFX_PREC_BF16 && c.e->use_tc && c.e->fuse_pair && Co == 64;
+    void* a_cur = A0; void* a_nxt = Hh;
     int dil = 1;
     for (int i = 0; i < 8; ++i, dil *= 3) {
       snprintf(name, sizeof(name), "voc.rs%d.l%d", j, i);
       const std::string p(name);
+      if (fuse_pairs) {
+        vfx_pair_desc pd;
+        memset(&pd, 0, sizeof(pd));
+        pd.a = a_cur; pd.x = X; pd.dilation = dil; pd.B = B; pd.L = (int)Lout; pd.C = Co;
+        pd.w1 = getw(c, p + ".c1.w", (size_t)3 * Co * Co, prec); pd.b1 = getf(c, p + ".c1.b", Co);
+        pd.w2 = getw(c, p + ".c2.w", (size_t)3 * Co * Co, prec); pd.b2 = getf(c, p + ".c2.b", Co);
+        pd.write_raw = (i < 7 || j == 3) ? 1 : 0;           // the next up-sampler consumes the operand only
+        if (i < 7) { pd.out_act = a_nxt; pd.act = VFX_ACT_LRELU; pd.act_param = 0.01f; }
+        else if (j < 3) { pd.out_act = U; pd.act = VFX_ACT_LRELU_XSINX; pd.act_param = 0.2f; }
+        if (!c.dry && c.rc == VFX_OK) {
+          char pt[48];
+          snprintf(pt, sizeof(pt), "voc.rs%d.pair", j);
+          char ptd[64];
+          snprintf(ptd, sizeof(ptd), "%s.d%d", pt, dil);
+          const double els = (double)B * Lout * Co;
+          // algorithmic bytes of a pair: x in + x' out, fp32
+          ProfScope ps(c, c.e->profile > 1 ? ptd : pt, 2.0 * 2.0 * 3.0 * Co * els, 8.0 * els);
+          VFX_TRY(resstack_pair_tc(pd, c.st));
+        }
+        void* t = a_cur; a_cur = a_nxt; a_nxt = t;
+        continue;
+      }
       {
         vfx_conv_desc d = conv_base(A0, B, 1, (int)Lout, Co, getw(c, p + ".c1.w", (size_t)3 * Co * Co, prec), Co);
         d.ntaps = 3;
@@ -737,6 +764,7 @@ int vfx_engine_set_option(vfx_engine* e, const char* key, int value) {
   VFX_REQUIRE(e && key, "set_option: null argument");
   if (!strcmp(key, "use_tc")) { e->use_tc = value; return VFX_OK; }
   if (!strcmp(key, "profile")) { e->profile = value; return VFX_OK; }
+  if (!strcmp(key, "fuse_pair")) { e->fuse_pair = value; return VFX_OK; }
   set_error("set_option: unknown key '%s'", key);
   return VFX_ERR_INVALID;
 }
@@ -831,6 +859,20 @@ size_t vfx_workspace_bytes_frames(const vfx_engine* e, int B, int T) {
   VFX_REQUIRE((e)->parts & VFX_PART_ANALYSIS,                                            \
               "this engine holds the vocoder weights only (stand-alone Vocoder); the analysis module is not loaded")
 
+// Pre-flight: the same forward pass on a null allocator gives the exact workspace need of THIS call; a too-small
+// workspace is refused before the first launch (a bump allocator that overflows mid-sequence would alias buffers).
+#define VFX_PREFLIGHT(mode_, call_)                                                                       \
+  do {                                                                                                    \
+    Bump dry_(nullptr, 0);                                                                                \
+    Ctx c{e, nullptr, &dry_, true, (mode_)};                                                              \
+    int r_ = (call_);                                                                                     \
+    if (r_ != VFX_OK) return r_;                                                                          \
+    if (dry_.peak > workspace_bytes) {                                                                    \
+      set_error("workspace too small: %zu bytes given, this call needs %zu", (size_t)workspace_bytes, dry_.peak); \
+      return VFX_ERR_WORKSPACE;                                                                           \
+    }                                                                                                     \
+  } while (0)
+
 #define VFX_FINISH(c, ws)                                                                \
   if ((ws).overflow) { set_error("workspace too small: need %zu bytes", (ws).peak); return VFX_ERR_WORKSPACE; } \
   return (c).rc
@@ -850,6 +892,7 @@ int vfx_analysis(vfx_engine* e, const float* mel, int B, int T, int mode, const 
   VFX_NEED_ANALYSIS(e);
   VFX_REQUIRE(mel && mel_log_out && B > 0 && T > 0 && workspace, "analysis: bad arguments");
   VFX_REQUIRE(mode == VFX_MODE_EVAL || mode == VFX_MODE_TRAIN_BN, "analysis: bad mode %d", mode);
+  VFX_PREFLIGHT(mode, analysis_forward(c, mel, B, T, nullptr, mel_log_out));
   Bump ws(workspace, workspace_bytes);
   Ctx c{e, (cudaStream_t)stream, &ws, false, mode};
   int r = analysis_forward(c, mel, B, T, drop_masks, mel_log_out);
@@ -861,6 +904,7 @@ int vfx_vocoder(vfx_engine* e, const float* mel, int B, int T, int input_is_log,
                 float scale, void* workspace, size_t workspace_bytes, void* stream) {
   VFX_ENTER(e);
   VFX_REQUIRE(mel && wav_out && B > 0 && T > 0 && workspace, "vocoder: bad arguments");
+  VFX_PREFLIGHT(VFX_MODE_EVAL, vocoder_forward(c, mel, B, T, input_is_log, wav_out, trim_len, scale));
   Bump ws(workspace, workspace_bytes);
   Ctx c{e, (cudaStream_t)stream, &ws, false, VFX_MODE_EVAL};
   int r = vocoder_forward(c, mel, B, T, input_is_log, wav_out, trim_len, scale);
@@ -872,6 +916,7 @@ int vfx_vocoder_cond(vfx_engine* e, const float* cond, int B, int Tc, float* wav
                      void* workspace, size_t workspace_bytes, void* stream) {
   VFX_ENTER(e);
   VFX_REQUIRE(cond && wav_out && B > 0 && Tc >= 4 && workspace, "vocoder_cond: bad arguments");
+  VFX_PREFLIGHT(VFX_MODE_EVAL, (dry_.raw((size_t)B * Tc * 128 * e->esz()), vocoder_generator(c, nullptr, B, Tc, wav_out, trim_len, scale)));
   Bump ws(workspace, workspace_bytes);
   Ctx c{e, (cudaStream_t)stream, &ws, false, VFX_MODE_EVAL};
   void* op = ws.raw((size_t)B * Tc * 128 * e->esz());
@@ -890,6 +935,7 @@ int vfx_restore(vfx_engine* e, const float* wav, int B, int L, int mode, const u
   VFX_REQUIRE(wav && wav_out && B > 0 && workspace, "restore: bad arguments");
   VFX_REQUIRE(mode == VFX_MODE_EVAL || mode == VFX_MODE_TRAIN_BN, "restore: bad mode %d", mode);
   VFX_REQUIRE(L > 1024, "restore: L=%d must exceed 1024 samples", L);
+  VFX_PREFLIGHT(mode, restore_forward(c, wav, B, L, nullptr, wav_out));
   Bump ws(workspace, workspace_bytes);
   Ctx c{e, (cudaStream_t)stream, &ws, false, mode};
   int r = restore_forward(c, wav, B, L, drop_masks, wav_out);
@@ -911,6 +957,13 @@ int vfx_conv_gemm(int precision, int impl, const vfx_conv_desc* d, void* stream)
     return conv_gemm_tc(precision, *d, (cudaStream_t)stream);
   }
   return conv_gemm_simt(precision, *d, (cudaStream_t)stream);
+}
+
+int vfx_resstack_pair(const vfx_pair_desc* d, void* stream) {
+  VFX_REQUIRE(d, "resstack_pair: null descriptor");
+  int r = resstack_pair_tc(*d, (cudaStream_t)stream);
+  if (r == VFX_ERR_UNSUPPORTED) set_error("resstack_pair: unsupported shape (C must be 64, 16-byte aligned tensors)");
+  return r;
 }
 
 int vfx_gru_layer(const float* gi, const float* whh_t, const float* bhh, int B, int T, float* out, void* stream) {

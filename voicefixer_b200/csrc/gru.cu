@@ -186,10 +186,12 @@ template <int G>
 int launch(const float* gi, const float* whh_t, const float* bhh, int B, int T, float* out, cudaStream_t st) {
   const int groups = (B + G - 1) / G;
   const size_t smem = sizeof(float) * (2 * G * H + 2 * KQ * G * RPC) + 16;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_set[64] = {false};           // per device: the attribute belongs to the device's copy of the function
+  int dev = 0;
+  VFX_CUDA_CHECK(cudaGetDevice(&dev));
+  if (dev >= 64 || !attr_set[dev]) {
     VFX_CUDA_CHECK(cudaFuncSetAttribute(gru_cluster_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set = true;
+    if (dev < 64) attr_set[dev] = true;
   }
   gru_cluster_kernel<G><<<2 * groups * CL, NT, smem, st>>>(gi, whh_t, bhh, B, T, out);
   VFX_LAUNCH_CHECK();

@@ -22,9 +22,11 @@ def _stream():
 
 
 def default_precision():
-    """"bf16" (tcgen05 tensor-core path, the production mode: meets the reference's own 1e-2 mean-abs acceptance bar with 4x
-    margin) unless VFX_PRECISION=fp32 selects the SIMT fp32 validation path (reference-exact to ~4e-6 relative RMS)."""
-    return os.environ.get("VFX_PRECISION", "bf16")
+    """"tf32": tcgen05 kind::tf32 on tf32-rounded fp32 operands -- the arithmetic class of the reference's own CUDA path
+    (cuDNN TF32 convolutions; waveform within 2e-3 relative RMS of the fp32 CPU path).  VFX_PRECISION selects another mode:
+    "bf16" (tcgen05 kind::f16, 1.6x faster, 1.3e-2 relative RMS / 2.7e-3 mean-abs: inside the reference's own 1e-2 mean-abs
+    acceptance bar) or "fp32" (SIMT fp32 validation path, reference-exact to ~4e-6)."""
+    return os.environ.get("VFX_PRECISION", "tf32")
 
 
 class Planner:
@@ -147,9 +149,17 @@ class Engine:
             raise _lib.VfxError("workspace query returned 0: the shape is out of range (restore() needs L > 1024 samples) or this "
                                 "engine holds the vocoder weights only (stand-alone Vocoder: restore/analysis are unavailable)")
         if self._ws is None or self._ws.numel() < nbytes:
-            self._ws = None
+            self._ws = None     # (captured graphs own their workspace tensors; see make_graph)
             self._ws = torch.empty(nbytes, dtype=torch.uint8, device=f"cuda:{self.device}")
         return self._ws
+
+    def max_batch(self, L, cap=64, reserve=2 << 30):
+        """Largest number of equal-length items (<= cap) whose restore() workspace fits the memory that is free right now
+        (plus the workspace this engine already holds), keeping `reserve` bytes back.  At least 1."""
+        free, _ = torch.cuda.mem_get_info(self.device)
+        avail = free + (self._ws.numel() if self._ws is not None else 0) - reserve
+        per_item = max(1, self.workspace_bytes(2, L) - self.workspace_bytes(1, L))
+        return int(max(1, min(cap, avail // per_item)))
 
     def workspace_bytes(self, B, L):
         return int(self.lib.vfx_workspace_bytes(self.h, B, L))
@@ -209,13 +219,14 @@ class Engine:
                                              ws.numel(), _stream()), "vfx_vocoder_cond")
         return out
 
-    def restore(self, wav, mode=0, drop_masks=None, out=None):
+    def restore(self, wav, mode=0, drop_masks=None, out=None, ws=None):
         """wav (B, L) on device -> restored wav (B, L) on device (one launch sequence)."""
         wav = self._dev(wav)
         B, L = wav.shape
         if out is None:
             out = torch.empty_like(wav)
-        ws = self._workspace(self.workspace_bytes(B, L))
+        if ws is None:
+            ws = self._workspace(self.workspace_bytes(B, L))
         dm = None
         if drop_masks is not None:
             dm = drop_masks.to(device=wav.device, dtype=torch.uint8).contiguous()
@@ -228,17 +239,20 @@ class Engine:
         CUDA graph; returns an object whose .replay() re-runs it (inputs are read from `wav`, results land in
         `out`).  Shapes, buffers and the workspace are frozen into the graph."""
         assert wav.is_cuda and out.is_cuda and wav.shape == out.shape
-        self._workspace(self.workspace_bytes(*wav.shape))           # allocate before capture
+        # the graph bakes raw device pointers in: it gets its OWN workspace, and the returned object keeps every
+        # buffer it touches alive (a later, larger call may replace the engine's shared workspace)
+        ws = torch.empty(self.workspace_bytes(*wav.shape), dtype=torch.uint8, device=wav.device)
         side = torch.cuda.Stream(device=wav.device)
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):                                # warm-up: one-time attribute / table setup
             for _ in range(2):
-                self.restore(wav, mode=mode, out=out)
+                self.restore(wav, mode=mode, out=out, ws=ws)
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g):
-            self.restore(wav, mode=mode, out=out)
+            self.restore(wav, mode=mode, out=out, ws=ws)
+        g._keep = (ws, wav, out, self.arena)
         return g
 
     def hf_cut(self, wav, ratio=0.95):
