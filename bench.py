@@ -248,6 +248,59 @@ def wl_vocoder(vf, steps=10):
             "api_host_to_host": {"value": 10.0 / (ms_api * 1e-3), "ms_per_call": ms_api, "out_shape": list(y.shape)}}
 
 
+def wl_stream(vf, seconds=12.0, chunk=1.0, ctx=0.5):
+    """SURVEY 8f-3 streaming path: VoiceFixer.restore_stream fed 0.1 s blocks; per-window compute time (host -> host, B = 1)
+    and the resulting time to the first restored audio = (chunk + context) seconds of arrival + one window's compute."""
+    from voicefixer_b200 import synthetic
+    wav = synthetic.make_utterances(1, seconds=seconds, seed=91)[0]
+    blocks = [wav[i:i + 4410] for i in range(0, len(wav), 4410)]
+    list(vf.restore_stream(blocks[:40], chunk_seconds=chunk, context_seconds=ctx))          # warm-up (workspace, lazy init)
+    gaps, n, t_prev = [], 0, time.perf_counter()
+    for y in vf.restore_stream(blocks, chunk_seconds=chunk, context_seconds=ctx):
+        t = time.perf_counter()
+        gaps.append((t - t_prev) * 1e3); t_prev = t; n += len(y)
+    steady = sorted(gaps[1:-1])[len(gaps[1:-1]) // 2] if len(gaps) > 2 else gaps[0]
+    return {"workload": f"restore_stream: {seconds:g} s fed in 0.1 s blocks, chunk {chunk:g} s + {ctx:g} s context each side (B = 1 windows)",
+            "compute_ms_per_window": steady, "first_window_compute_ms": gaps[0],
+            "time_to_first_audio_ms": (chunk + ctx) * 1e3 + gaps[0], "real_time_factor": chunk * 1e3 / steady,
+            "samples_out": n, "samples_in": int(len(wav))}
+
+
+def wl_cli(precision, n_files=8, seconds=10.0):
+    """the CLI `python -m voicefixer_b200 --infolder .. --outfolder ..` (mirror of voicefixer/__main__.py) on a
+    folder of wav files: disk -> decode -> GPU -> encode -> disk, checkpoints read from ~/.cache/voicefixer like the reference.
+    Wall time of main() includes the one-off checkpoint load; `jobs_wall_s` is the pipeline alone."""
+    import contextlib, io, re, tempfile
+    from voicefixer_b200 import synthetic, wavio
+    from voicefixer_b200.__main__ import main as cli_main
+    old_home, old_prec = os.environ.get("HOME"), os.environ.get("VFX_PRECISION")
+    with tempfile.TemporaryDirectory() as td:
+        try:
+            os.environ["HOME"], os.environ["VFX_PRECISION"] = td, precision
+            synthetic.write_checkpoints(td, seed=0)
+            src, dst = os.path.join(td, "in"), os.path.join(td, "out")
+            os.makedirs(src)
+            wavs = synthetic.make_utterances(n_files, seconds=seconds, seed=95)
+            for i, w in enumerate(wavs):
+                wavio.save_wave(w[None], os.path.join(src, f"u{i:02d}.wav"))
+            buf = io.StringIO()
+            t0 = time.perf_counter()
+            with contextlib.redirect_stdout(buf):
+                rc = cli_main(["--infolder", src, "--outfolder", dst])
+            wall = time.perf_counter() - t0
+            m = re.search(r"Done: (\d+) job\(s\) in ([0-9.]+) s", buf.getvalue())
+            jobs_wall = float(m.group(2)) if m else None
+            ok = rc == 0 and len(os.listdir(dst)) == n_files
+        finally:
+            if old_home is None: os.environ.pop("HOME", None)
+            else: os.environ["HOME"] = old_home
+            if old_prec is None: os.environ.pop("VFX_PRECISION", None)
+            else: os.environ["VFX_PRECISION"] = old_prec
+    return {"workload": f"CLI folder mode: {n_files} x {seconds:g} s wav files, disk -> GPU -> disk, one utterance per launch sequence "
+                        "(reference semantics), reader / writer threads", "ok": ok, "wall_s_including_checkpoint_load": wall,
+            "jobs_wall_s": jobs_wall, "value": (n_files * seconds / jobs_wall) if jobs_wall else None, "unit": UNIT}
+
+
 def csrc_sha():
     """Hash of the CUDA sources: an ncu traffic figure is only quoted when it was captured from these sources."""
     import hashlib
@@ -570,6 +623,10 @@ def main():
             workloads["longform"] = wl_longform(vf)
         except Exception as e:
             workloads["longform"] = {"error": f"{type(e).__name__}: {e}"}
+        try:
+            workloads["stream"] = wl_stream(vf)
+        except Exception as e:
+            workloads["stream"] = {"error": f"{type(e).__name__}: {e}"}
     # free the headline engine before the next ones
     res.pop("vf"); res.pop("eng"); res.pop("rep")
     import gc
@@ -595,6 +652,11 @@ def main():
             del r2
         except Exception as e:
             modes[other] = {"error": f"{type(e).__name__}: {e}"}
+        gc.collect(); torch.cuda.empty_cache()
+        try:
+            workloads["cli_folder"] = wl_cli(prec)
+        except Exception as e:
+            workloads["cli_folder"] = {"error": f"{type(e).__name__}: {e}"}
         gc.collect(); torch.cuda.empty_cache()
         try:
             lib_base = torch_gpu_result(args, B)

@@ -149,6 +149,13 @@ typedef struct vfx_conv_desc {
   float act_param;          /* leaky slope */
   const float* act_scale;   /* optional per-channel affine before the activation of out_act:          */
   const float* act_shift;   /* out_act = act(result * act_scale[n] + act_shift[n]) (fused eval-mode BN) */
+  /* TF32 "encoded stream" (vocoder ResStacks in VFX_PREC_TF32): ONE fp32 tensor S serves both as the next convolution's
+   * tf32 operand and as the lossless carrier of the fp32 residual stream:  S = bits(lrelu(x, enc_slope)) + 0x1000.
+   * kind::tf32 ignores the low 13 mantissa bits of an operand, so reading S as an operand yields exactly
+   * round-to-nearest-tf32(lrelu(x)); subtracting 0x1000 from the bits and inverting the (bijective) leaky ReLU gives x back.
+   * res_enc: `residual` holds S, it is decoded before the add.  raw_enc: `out_raw` receives S of the result. */
+  int res_enc, raw_enc;
+  float enc_slope;
 } vfx_conv_desc;
 
 enum vfx_act { VFX_ACT_NONE = 0, VFX_ACT_LRELU = 1, VFX_ACT_ELU = 2,

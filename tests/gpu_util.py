@@ -6,7 +6,8 @@ from voicefixer_b200 import _lib
 
 def conv_gemm(a, w, taps, Hq=None, Wq=None, N=None, w_off=None, bias=None, bias_mod=None, residual=None,
               act="none", act_param=0.0, want_raw=True, want_act=False, sh=1, rh=0, sw=1, rw=0, OH=None, OW=None,
-              out_ld=None, out_col=0, precision="fp32", impl=0, out_raw=None, out_act=None):
+              out_ld=None, out_col=0, precision="fp32", impl=0, out_raw=None, out_act=None, res_enc=0, raw_enc=0,
+              enc_slope=0.0):
     """a: (B,H,W,Cin) cuda (fp32 or bf16); w: flat weight tensor; taps: [(dh,dw)]."""
     lib = _lib.load()
     B, H, W, Cin = a.shape
@@ -39,6 +40,7 @@ def conv_gemm(a, w, taps, Hq=None, Wq=None, N=None, w_off=None, bias=None, bias_
         d.residual = residual.data_ptr()
         d.r_sW, d.r_sH, d.r_sB, d.r_col = residual.stride(2), residual.stride(1), residual.stride(0), 0
     d.act = _lib.ACT[act]; d.act_param = act_param
+    d.res_enc, d.raw_enc, d.enc_slope = res_enc, raw_enc, enc_slope
     st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
     _lib.check(lib.vfx_conv_gemm(_lib.PREC[precision], impl, ctypes.byref(d), st), "vfx_conv_gemm")
     torch.cuda.synchronize()

@@ -379,3 +379,57 @@ def test_wav_reader_formats_beyond_stdlib_wave(tmp_path):
     (tmp_path / "junk.wav").write_bytes(b"OggS" + bytes(64))
     with pytest.raises(RuntimeError, match="not a RIFF/WAVE"):
         wavio.load_mono(str(tmp_path / "junk.wav"))
+
+
+# ---------------------------------------------------------------------------- restore_stream windowing (no GPU: fake engine)
+class _EchoEngine:
+    """Stands in for the CUDA engine: restore() returns its input and records the window lengths."""
+    device = 0
+    arena = None
+
+    def __init__(self):
+        self.windows = []
+
+    def restore(self, x, mode=0):
+        self.windows.append(int(x.shape[1]))
+        return x.clone()
+
+
+def _stream_vf(monkeypatch):
+    import torch
+    from voicefixer_b200 import api
+    monkeypatch.setattr(api, "_check_cuda", lambda cuda: None)
+    real_to = torch.Tensor.to
+    monkeypatch.setattr(torch.Tensor, "to", lambda self, *a, **k: self if (a and isinstance(a[0], str) and a[0].startswith("cuda")) else real_to(self, *a, **k))
+    eng = _EchoEngine()
+    return api.VoiceFixer.from_engine(eng), eng
+
+
+@pytest.mark.parametrize("n,blk,chunk,ctx", [(200000, 4410, 1.0, 0.5), (200000, 100000, 1.0, 0.0), (44100 * 3 + 17, 999, 0.5, 0.25),
+                                             (50000, 50000, 2.0, 1.0), (1500, 700, 1.0, 1.0)])
+def test_restore_stream_covers_the_input_exactly_once(monkeypatch, n, blk, chunk, ctx):
+    """With an identity engine the concatenated stream output must be the input: every sample emitted exactly once, in
+    order, whatever the block sizes; no window shorter than the front end's reflect pad allows."""
+    vf, eng = _stream_vf(monkeypatch)
+    rs = np.random.RandomState(0)
+    x = rs.randn(n).astype(np.float32)
+    out = list(vf.restore_stream((x[i:i + blk] for i in range(0, n, blk)), chunk_seconds=chunk, context_seconds=ctx))
+    y = np.concatenate(out)
+    assert y.shape == x.shape and np.array_equal(y, x)
+    assert min(eng.windows) > 1024
+    C, X = int(round(chunk * 44100)), int(round(ctx * 44100))
+    assert max(eng.windows) <= C + 2 * X or n <= C + 2 * X
+    full = [w for w in eng.windows if w == C + 2 * X]
+    assert len(full) >= max(0, (n - X) // C - 2)                       # steady state: fixed-size windows
+
+
+def test_restore_stream_30s_windows_are_the_reference_segments(monkeypatch):
+    """chunk 30 s, no context: the windows are exactly restore_inmem's segments (voicefixer/base.py:116-119)."""
+    vf, eng = _stream_vf(monkeypatch)
+    n = 44100 * 65 + 123
+    x = np.zeros(n, np.float32)
+    out = list(vf.restore_stream([x[:1000000], x[1000000:]], chunk_seconds=30.0, context_seconds=0.0))
+    assert eng.windows == [44100 * 30, 44100 * 30, 44100 * 5 + 123]
+    assert [len(o) for o in out] == eng.windows
+    with pytest.raises(ValueError):
+        list(vf.restore_stream([x], chunk_seconds=0))

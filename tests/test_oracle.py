@@ -103,6 +103,33 @@ def test_slaney_basis_matches_torchaudio_formula():
     assert np.max(np.abs(O.slaney_htk_mel_basis() - ref)) < 2e-6
 
 
+@pytest.mark.skipif(not os.path.isdir("/root/reference/voicefixer"), reason="reference checkout not present (GPU box)")
+def test_slaney_basis_matches_the_reference_melscale_fbanks():
+    """The one independent cross-check of Vocoder.oracle()'s mel basis that exists offline (librosa is absent): the
+    reference's OWN implementation of the same filterbank, melscale_fbanks(..., norm="slaney", mel_scale="htk")
+    (voicefixer/tools/mel_scale.py:173-238, Slaney branch :226-229), imported unmodified from /root/reference and
+    run here -- against both the oracle's and the product's (wavio) restatement of librosa.filters.mel."""
+    import subprocess, sys, json
+    code = (
+        "import sys, json, numpy as np; sys.path.insert(0, %r)\n"
+        "from ref_loader import install; install()\n"
+        "from voicefixer.tools.mel_scale import melscale_fbanks\n"
+        "fb = melscale_fbanks(1025, 0.0, 22050.0, 128, 44100, norm='slaney', mel_scale='htk')\n"
+        "np.save(sys.argv[1], fb.numpy())\n") % os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    import tempfile
+    with tempfile.TemporaryDirectory() as td:
+        out = os.path.join(td, "fb.npy")
+        r = subprocess.run([sys.executable, "-c", code, out], capture_output=True, text=True, timeout=120)
+        assert r.returncode == 0, r.stderr[-2000:]
+        ref = np.load(out).T                                        # (128, 1025) like librosa.filters.mel
+    from voicefixer_b200 import wavio
+    assert ref.shape == (128, 1025)
+    scale = float(np.max(np.abs(ref)))
+    assert np.max(np.abs(O.slaney_htk_mel_basis() - ref)) < 2e-6 * max(1.0, scale / 1e-2)
+    assert np.max(np.abs(wavio.slaney_htk_mel_basis() - ref)) < 2e-6 * max(1.0, scale / 1e-2)
+    assert np.max(np.abs(wavio.slaney_htk_mel_basis() - ref)) / scale < 1e-4      # fp32 (reference) vs float64 build
+
+
 @pytest.mark.timeout(900)
 @pytest.mark.skipif(not os.path.isdir("/root/reference/voicefixer"), reason="reference checkout not present (GPU box)")
 def test_oracle_live_against_unmodified_reference_on_fresh_inputs():

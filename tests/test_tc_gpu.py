@@ -147,3 +147,40 @@ def test_tc_wide_n_and_k7_valid_conv(prec):
     wp = w.permute(2, 0, 1).contiguous()
     raw, _ = conv_gemm(a, wp, [(0, k) for k in range(7)], Wq=L, OW=L, precision=prec, impl=1)
     assert rel_rms(raw[:, 0].permute(0, 2, 1).cpu(), ref.cpu()) < 2e-5
+
+
+def _enc(x, slope=0.01):
+    """host form of the encoded tf32 stream: S = bits(lrelu(x)) + 0x1000 (include/vfx_b200.h)."""
+    y = F.leaky_relu(x, slope).contiguous()
+    return (y.view(torch.int32) + 0x1000).view(torch.float32)
+
+
+def _dec(s, slope=0.01):
+    y = (s.contiguous().view(torch.int32) - 0x1000).view(torch.float32)
+    return torch.where(y > 0, y, y / slope)
+
+
+@pytest.mark.parametrize("impl", [0, 1])
+@pytest.mark.parametrize("C,L,dil", [(64, 3000, 3), (128, 1000, 1), (256, 500, 243)])
+def test_tf32_encoded_stream(C, L, dil, impl):
+    """One fp32 tensor S as tf32 operand AND lossless residual carrier.  The UN-rounded S goes to the tensor core: this
+    passes only if kind::tf32 ignores the low 13 mantissa bits (then the operand it sees is round-to-nearest(lrelu(x)))."""
+    from gpu_util import conv_gemm
+    from voicefixer_b200.weights import round_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    B = 2
+    x = _rnd(B, L, C, seed=31)
+    S = _enc(x)
+    assert torch.equal((S.view(torch.int32) & ~0x1FFF).view(torch.float32), round_tf32(F.leaky_relu(x, 0.01).cpu()).to(DEV))
+    assert rel_rms(_dec(S).cpu(), x.cpu()) < 2e-7                       # the residual survives the encoding
+    w, wf = _op(_rnd(C, C, 3, seed=32, scale=0.1), "tf32")
+    b = _rnd(C, seed=33)
+    a_ref = round_tf32(F.leaky_relu(x, 0.01).cpu()).to(DEV)
+    ref = F.conv1d(a_ref.permute(0, 2, 1), wf, b, dilation=dil, padding=dil).permute(0, 2, 1) + x
+    buf = S.clone()[:, None].contiguous()
+    raw, _ = conv_gemm(buf, w.permute(2, 0, 1).contiguous(), [(0, -dil), (0, 0), (0, dil)], bias=b, residual=buf,
+                       out_raw=torch.empty_like(buf), res_enc=1, raw_enc=1, enc_slope=0.01, precision="tf32", impl=impl)
+    assert rel_rms(_dec(raw[:, 0]).cpu(), ref.cpu()) < 2e-5
+    # and as the next operand it is exactly round-to-nearest(lrelu(result))
+    got_op = (raw[:, 0].contiguous().view(torch.int32) & ~0x1FFF).view(torch.float32)
+    assert rel_rms(got_op.cpu(), F.leaky_relu(ref, 0.01).cpu()) < 5e-4

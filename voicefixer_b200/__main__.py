@@ -173,7 +173,7 @@ def main(argv=None):
              load=lambda src: vf._load_wav(src, sample_rate=44100),          # base.py:141-146, staged
              restore=lambda wav, mode: vf.restore_inmem(wav, cuda=not args.disable_cuda, mode=mode),
              save=lambda out, dst: wavio.save_wave(out, fname=dst, sample_rate=44100), say=say)
-    say("Done: {} job(s) in {} s".format(len(jobs), round(time.time() - t0, 1)))
+    say("Done: {} job(s) in {} s".format(len(jobs), round(time.time() - t0, 3)))
     return 0
 
 

@@ -29,6 +29,7 @@ class ConvDesc(ctypes.Structure):
         ("bias", _vp), ("bias_mod", _i),
         ("residual", _vp), ("r_sB", _ll), ("r_sH", _ll), ("r_sW", _ll), ("r_col", _i),
         ("act", _i), ("act_param", _f), ("act_scale", _vp), ("act_shift", _vp),
+        ("res_enc", _i), ("raw_enc", _i), ("enc_slope", _f),
     ]
 
 

@@ -143,10 +143,13 @@ __global__ void __launch_bounds__(NT) conv_gemm_simt_kernel(const vfx_conv_desc 
       if (n >= d.N) continue;
       float v = acc[i][j];
       if (d.bias) v += d.bias[n % d.bias_mod];
-      if (d.residual)
-        v += d.residual[(long long)b * d.r_sB + (long long)oh * d.r_sH + (long long)ow * d.r_sW + d.r_col + n];
+      if (d.residual) {
+        const float r = d.residual[(long long)b * d.r_sB + (long long)oh * d.r_sH + (long long)ow * d.r_sW + d.r_col + n];
+        v += d.res_enc ? stream_dec(r, 1.0f / d.enc_slope) : r;
+      }
       if (d.out_raw)
-        d.out_raw[(long long)b * d.o_sB + (long long)oh * d.o_sH + (long long)ow * d.o_sW + d.o_col + n] = v;
+        d.out_raw[(long long)b * d.o_sB + (long long)oh * d.o_sH + (long long)ow * d.o_sW + d.o_col + n] =
+            d.raw_enc ? stream_enc(v, d.enc_slope) : v;
       if (out_act) {
         const float va = d.act_scale ? fmaf(v, d.act_scale[n], d.act_shift[n]) : v;
         out_act[(long long)b * d.oa_sB + (long long)oh * d.oa_sH + (long long)ow * d.oa_sW + d.oa_col + n] =

@@ -65,6 +65,8 @@ struct TcParams {
   uint32_t a_stage_bytes, b_stage_bytes;
   uint32_t row_bytes;       // bytes of one K-chunk row: KC * element size (128, or 64 for bf16 KC = 32)
   uint32_t at_bytes;        // TMA epilogue: bytes of one activated-operand staging tile (32 rows x 32 columns)
+  uint32_t res_enc, raw_enc;           // encoded tf32 stream (vfx_conv_desc): decode the residual / encode the raw output
+  float enc_slope, enc_inv_slope;
   uint32_t epi_warps;       // TMA epilogue: warps that own staging (4 when the tile has one 32-column chunk: the odd-chunk warps idle)
   uint32_t at_double;       // ... double-buffered (bf16) or single (tf32: see the wait before it is rewritten)
   uint32_t sbo16;           // stride-byte-offset >> 4 of the K-major swizzled layout (8 rows)
@@ -402,14 +404,26 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         if (has_res) {
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
-            const float4 r4 = *reinterpret_cast<const float4*>(ro + ((uint32_t)(j << 4) ^ sw128));
+            float4 r4 = *reinterpret_cast<const float4*>(ro + ((uint32_t)(j << 4) ^ sw128));
+            if (p.res_enc) {
+              r4.x = stream_dec(r4.x, p.enc_inv_slope); r4.y = stream_dec(r4.y, p.enc_inv_slope);
+              r4.z = stream_dec(r4.z, p.enc_inv_slope); r4.w = stream_dec(r4.w, p.enc_inv_slope);
+            }
             f[4 * j] += r4.x; f[4 * j + 1] += r4.y; f[4 * j + 2] += r4.z; f[4 * j + 3] += r4.w;
           }
         }
         if (p.out_raw) {
+          if (p.raw_enc) {
 #pragma unroll
-          for (int j = 0; j < 8; ++j)
-            *reinterpret_cast<float4*>(ro + ((uint32_t)(j << 4) ^ sw128)) = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+            for (int j = 0; j < 8; ++j)
+              *reinterpret_cast<float4*>(ro + ((uint32_t)(j << 4) ^ sw128)) =
+                  make_float4(stream_enc(f[4 * j], p.enc_slope), stream_enc(f[4 * j + 1], p.enc_slope),
+                              stream_enc(f[4 * j + 2], p.enc_slope), stream_enc(f[4 * j + 3], p.enc_slope));
+          } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              *reinterpret_cast<float4*>(ro + ((uint32_t)(j << 4) ^ sw128)) = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+          }
         }
         if (p.out_act) {
           uint8_t* const at_tile = at_base + (p.at_double ? k * p.at_bytes : 0u);
@@ -544,13 +558,25 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           if (has_res) {
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-              f[4 * j] += rcur[j].x; f[4 * j + 1] += rcur[j].y; f[4 * j + 2] += rcur[j].z; f[4 * j + 3] += rcur[j].w;
+              float4 r4 = rcur[j];
+              if (p.res_enc) {
+                r4.x = stream_dec(r4.x, p.enc_inv_slope); r4.y = stream_dec(r4.y, p.enc_inv_slope);
+                r4.z = stream_dec(r4.z, p.enc_inv_slope); r4.w = stream_dec(r4.w, p.enc_inv_slope);
+              }
+              f[4 * j] += r4.x; f[4 * j + 1] += r4.y; f[4 * j + 2] += r4.z; f[4 * j + 3] += r4.w;
             }
           }
           if (p.out_raw) {
             float4* op = reinterpret_cast<float4*>(p.out_raw + off_o + c0);
+            if (p.raw_enc) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) op[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+              for (int j = 0; j < 8; ++j)
+                op[j] = make_float4(stream_enc(f[4 * j], p.enc_slope), stream_enc(f[4 * j + 1], p.enc_slope),
+                                    stream_enc(f[4 * j + 2], p.enc_slope), stream_enc(f[4 * j + 3], p.enc_slope));
+            } else {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) op[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+            }
           }
           if (p.out_act) {
             if (p.act_scale) {
@@ -657,6 +683,9 @@ int conv_gemm_tc(int precision, const vfx_conv_desc& d, cudaStream_t st) {
   p.bias = d.bias; p.bias_mod = d.bias_mod > 0 ? d.bias_mod : d.N;
   p.residual = d.residual; p.r_sB = d.r_sB; p.r_sH = d.r_sH; p.r_sW = d.r_sW; p.r_col = d.r_col;
   p.act = d.act; p.act_param = d.act_param;
+  p.res_enc = (d.residual && d.res_enc) ? 1u : 0u; p.raw_enc = (d.out_raw && d.raw_enc) ? 1u : 0u;
+  if ((p.res_enc || p.raw_enc) && !(d.enc_slope > 0.f)) { set_error("conv_gemm_tc: enc_slope must be positive"); return VFX_ERR_INVALID; }
+  p.enc_slope = d.enc_slope; p.enc_inv_slope = d.enc_slope > 0.f ? 1.0f / d.enc_slope : 0.f;
   p.act_scale = d.out_act ? d.act_scale : nullptr; p.act_shift = d.out_act ? d.act_shift : nullptr;
   // instruction descriptor: c=F32 [4,6)=1, a/b format [7,10)/[10,13) = 1 (BF16) or 2 (TF32), K-major both,
   // N>>3 [17,23), M>>4 [24,29)
@@ -684,10 +713,11 @@ int conv_gemm_tc(int precision, const vfx_conv_desc& d, cudaStream_t st) {
   p.epi_arrivals = 32u * NUM_EPI_WARPS;
   const bool needs_ro = d.out_raw || d.residual;
   p.epi_at_off = needs_ro ? 8192u : 0u;
-  // activated-operand staging: bf16 2 x 2 KB (double-buffered); tf32 2 x 4 KB when it is the only output, one 4 KB tile
-  // next to the raw/residual tiles (8 warps x 16 KB would leave no room for the operand stages)
+  // activated-operand staging: bf16 2 x 2 KB (double-buffered); tf32 one 4 KB tile (8 warps x 16 KB next to the
+  // raw/residual tiles would leave no room for the operand stages)
   p.at_bytes = tf32 ? 4096u : 2048u;
-  p.at_double = (tf32 && needs_ro) ? 0u : 1u;
+  p.at_double = tf32 ? 0u : 1u;      // tf32: one tile (the freed 4 KB per warp buys another operand stage: conv1 of a C = 64 pair
+                                     // had two halo stages and ran latency-bound at 70 % of HBM)
   p.epi_warp_bytes = p.epi_at_off + (d.out_act ? p.at_bytes * (p.at_double ? 2u : 1u) : 0u);
   p.bias_floats = ((uint32_t)d.N + 63u) & ~63u;
   p.epi_warps = Ntile >= 64 ? (uint32_t)NUM_EPI_WARPS : 4u;       // warps 2..5 (chunk parity 0) are the only ones with work at Ntile = 32

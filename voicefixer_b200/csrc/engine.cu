@@ -41,6 +41,7 @@ struct vfx_engine {
   float2* d_tw = nullptr;       // exp(-2 pi i k / 2048), k < 1024
   std::vector<std::string> missing;
   int parts = 0;    // VFX_PART_* bits of the weight sets found complete by vfx_engine_finalize
+  int tf32_stream = 0;  // TF32: vocoder residual streams are kept as ONE encoded fp32 tensor (operand + residual carrier)
   int fuse_pair = 1;  // BF16: ResStack pairs of width 64 run as ONE fused kernel (resstack_pair_tc.cu)
   int profile = 0;
   std::vector<vfx::ProfRec> prof;
@@ -537,6 +538,9 @@ int vocoder_generator(Ctx& c, const void* cond, int B, int Tc, float* wav_out, i
     set_act(d, U, 1024, 0, VFX_ACT_LRELU_XSINX, 0.2f);
     VFX_TRY(run_conv(c, prec, d, "voc.pre"));
   }
+  // TF32 "encoded stream" (vfx_conv_desc.res_enc / raw_enc): X holds S = bits(lrelu(x)) + 0x1000, which conv1 reads as
+  // its tf32 operand and conv2 decodes as the fp32 residual -- no separate activated copy (24 -> 20 bytes per element and pair)
+  const bool enc = prec == VFX_PREC_TF32 && c.e->use_tc && c.e->tf32_stream;
   long long Lin = Tc;
   for (int j = 0; j < 4; ++j) {
     const int Ci = VOC_CIN[j], Co = VOC_COUT[j], u = VOC_U[j];
@@ -565,7 +569,8 @@ int vocoder_generator(Ctx& c, const void* cond, int B, int Tc, float* wav_out, i
         else          { d.dw[0] = 1; d.w_off[0] = 0;         d.dw[1] = 0;  d.w_off[1] = u * mat;         r0 = nA; }
         d.bias = bias; d.bias_mod = Co;
         set_raw(d, X, (long long)u * Co, r0 * Co);
-        set_act(d, A0, (long long)u * Co, r0 * Co, VFX_ACT_LRELU, 0.01f);
+        if (enc) { d.raw_enc = 1; d.enc_slope = 0.01f; }
+        else set_act(d, A0, (long long)u * Co, r0 * Co, VFX_ACT_LRELU, 0.01f);
         VFX_TRY(run_conv(c, prec, d, up_tag));
       }
     }
@@ -601,7 +606,8 @@ int vocoder_generator(Ctx& c, const void* cond, int B, int Tc, float* wav_out, i
         continue;
       }
       {
-        vfx_conv_desc d = conv_base(A0, B, 1, (int)Lout, Co, getw(c, p + ".c1.w", (size_t)3 * Co * Co, prec), Co);
+        vfx_conv_desc d = conv_base(enc ? (const void*)X : (const void*)A0, B, 1, (int)Lout, Co,
+                                    getw(c, p + ".c1.w", (size_t)3 * Co * Co, prec), Co);
         d.ntaps = 3;
         for (int k = 0; k < 3; ++k) { d.dw[k] = (k - 1) * dil; d.w_off[k] = (long long)k * Co * Co; }
         d.bias = getf(c, p + ".c1.b", Co);
@@ -616,9 +622,16 @@ int vocoder_generator(Ctx& c, const void* cond, int B, int Tc, float* wav_out, i
         for (int k = 0; k < 3; ++k) { d.dw[k] = k - 1; d.w_off[k] = (long long)k * Co * Co; }
         d.bias = getf(c, p + ".c2.b", Co);
         set_res(d, X, Co, 0);
-        set_raw(d, X, Co, 0);
-        if (i < 7) set_act(d, A0, Co, 0, VFX_ACT_LRELU, 0.01f);
-        else if (j < 3) set_act(d, U, Co, 0, VFX_ACT_LRELU_XSINX, 0.2f);   // act + next UpsampleNet's x+sin x
+        if (enc) {
+          d.res_enc = 1; d.enc_slope = 0.01f;
+          if (i < 7) { set_raw(d, X, Co, 0); d.raw_enc = 1; }               // S' in place
+          else if (j == 3) set_raw(d, X, Co, 0);                            // last stack: plain x' for the final conv
+          else set_act(d, U, Co, 0, VFX_ACT_LRELU_XSINX, 0.2f);             // next UpsampleNet's operand only
+        } else {
+          set_raw(d, X, Co, 0);
+          if (i < 7) set_act(d, A0, Co, 0, VFX_ACT_LRELU, 0.01f);
+          else if (j < 3) set_act(d, U, Co, 0, VFX_ACT_LRELU_XSINX, 0.2f);   // act + next UpsampleNet's x+sin x
+        }
         VFX_TRY(run_conv(c, prec, d, c2_tag));
       }
     }
@@ -765,6 +778,7 @@ int vfx_engine_set_option(vfx_engine* e, const char* key, int value) {
   if (!strcmp(key, "use_tc")) { e->use_tc = value; return VFX_OK; }
   if (!strcmp(key, "profile")) { e->profile = value; return VFX_OK; }
   if (!strcmp(key, "fuse_pair")) { e->fuse_pair = value; return VFX_OK; }
+  if (!strcmp(key, "tf32_stream")) { e->tf32_stream = value; return VFX_OK; }
   set_error("set_option: unknown key '%s'", key);
   return VFX_ERR_INVALID;
 }

@@ -20,9 +20,9 @@
 //                views of it; larger dilations: one 128-row box per tap, each its own pipeline stage
 //     warp 1     MMA issuer, software-pipelined: conv1(i), then conv2(i-1) while the h tile of i is being produced
 //     warp 2-5   epilogue 1: TMEM -> +b1 -> lrelu -> bf16 -> h tile (double-buffered)
-//     warp 6-9   epilogue 2: TMA-staged like conv_gemm_tc's: residual tile in by TMA (prefetched across tiles), fp32
-//                result written back in place + activated bf16 operand tile, TMA stores (30-row boxes for the
-//                last quarter of a tile)
+//     warp 6-9   epilogue 2: TMA-staged like conv_gemm_tc's: residual tiles in by TMA (ring of four, prefetched three
+//                32-column chunks ahead), fp32 result written back in place + activated bf16 operand tile, TMA stores
+//                (30-row boxes for the last quarter of a tile)
 //   TMEM: 4 accumulator stages of 64 columns for each convolution (512 columns).
 // * x is updated in place (a tile's residual rows are its own output rows); the operand copy `a` is read with a halo
 //   that neighbouring tiles overwrite, so the activated output goes to a different buffer (ping-pong in the engine).
@@ -97,8 +97,8 @@ resstack_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   uint64_t* const h_full = acc2_empty + PNACC;       // [2]
   uint64_t* const h_empty = h_full + 2;              // [2]
   uint64_t* const wfull = h_empty + 2;
-  uint64_t* const res_full = wfull + 1;              // [4 warps][2 buffers]
-  uint32_t* const tmem_slot = reinterpret_cast<uint32_t*>(res_full + 8);
+  uint64_t* const res_full = wfull + 1;              // [4 warps][4 ring slots]
+  uint32_t* const tmem_slot = reinterpret_cast<uint32_t*>(res_full + 16);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -112,7 +112,7 @@ resstack_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     }
     for (int a = 0; a < 2; ++a) { mbar_init(&h_full[a], 128); mbar_init(&h_empty[a], 1); }
     mbar_init(wfull, 1);
-    for (int i = 0; i < 8; ++i) mbar_init(&res_full[i], 1);
+    for (int i = 0; i < 16; ++i) mbar_init(&res_full[i], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -291,31 +291,44 @@ resstack_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     }
   } else {
     // ===================== epilogue 2: conv2 accumulator + b2 + residual -> x' (fp32) and act(x') (bf16) ============
+    // A warp walks the chunk stream n = 2 * tile + c (c = 32-column half).  Its residual tiles arrive by TMA in a ring of
+    // four 4 KB buffers, prefetched THREE chunks ahead (a DRAM round trip is longer than one chunk's work; with a
+    // one-chunk look-ahead the kernel ran at 4.4 TB/s, latency-bound in this role).  The fp32 result is written back in
+    // place and stored from the same buffer; ring slot (n + 3) % 4 = (n - 1) % 4 is free again once the store group of chunk
+    // n - 1 has been read out (wait_group.read 1 after committing chunk n's group).
     const int ew = warp - 6, sub = warp & 3;
-    uint8_t* const stg = staging + ew * p.epi_warp_bytes;       // [RO0 RO1 (4 KB each)] [AT0 AT1 (2 KB each, optional)]
-    uint8_t* const at_base = stg + 8192;
-    uint64_t* const rfull = res_full + ew * 2;
+    uint8_t* const stg = staging + ew * p.epi_warp_bytes;       // [RO0..RO3 (4 KB each)] [AT0 AT1 (2 KB each, optional)]
+    uint8_t* const at_base = stg + 16384;
+    uint64_t* const rfull = res_full + ew * 4;
     const int r0 = sub * 32;
     const CUtensorMap* const mO = sub == 3 ? &tmO30 : &tmO;     // rows 126/127 of a tile belong to the next tile
     const CUtensorMap* const mT = sub == 3 ? &tmT30 : &tmT;
-    uint32_t k = 0, rph = 0;
+    uint32_t rph = 0;                                           // bit b = phase of rfull[b]
     PTileIter it; it.init(p, blockIdx.x);
-    if (lane == 0 && n_my > 0) {
-      const PTile t = it.coord();
-      mbar_expect_tx(&rfull[0], 4096);
-      tma_load_4d(&tmR, &rfull[0], stg, 0, t.p0 + r0, 0, t.b);
+    PTileIter pit; pit.init(p, blockIdx.x);                     // tile of the next chunk to prefetch
+    uint32_t pn = 0;                                            // next chunk index to prefetch
+    const uint32_t n_chunks = 2 * n_my;
+#pragma unroll 1
+    for (; pn < 3 && pn < n_chunks; ++pn) {                     // bookkeeping is warp-uniform, lane 0 issues
+      if (lane == 0) {
+        const PTile t = pit.coord();
+        mbar_expect_tx(&rfull[pn & 3], 4096);
+        tma_load_4d(&tmR, &rfull[pn & 3], stg + (pn & 3) * 4096, (int)(pn & 1) * 32, t.p0 + r0, 0, t.b);
+      }
+      if (pn & 1) pit.next(p);
     }
     const uint32_t sw128 = (uint32_t)(lane & 7) << 4, sw64 = (uint32_t)((lane >> 1) & 3) << 4;
     for (uint32_t i = 0; i < n_my; ++i) {
       const PTile t = it.coord();
-      it.next(p);                                         // `it` now points at this CTA's next tile
+      it.next(p);
       mbar_wait(&acc2_full[i & (PNACC - 1)], (i / PNACC) & 1);
       tc_fence_after();
       const uint32_t t_row = tmem_base + ((uint32_t)(sub * 32) << 16) + PNACC * PC + (i & (PNACC - 1)) * PC;
 #pragma unroll 1
       for (int c = 0; c < 2; ++c) {
-        uint8_t* const ro = stg + k * 4096 + lane * 128;
-        mbar_wait(&rfull[k], (rph >> k) & 1); rph ^= 1u << k;
+        const uint32_t n = 2 * i + (uint32_t)c, slot = n & 3, k = n & 1;
+        uint8_t* const ro = stg + slot * 4096 + lane * 128;
+        mbar_wait(&rfull[slot], (rph >> slot) & 1); rph ^= 1u << slot;
         uint32_t v[32];
         tc_ld32(t_row + c * 32, v);
         float f[32];
@@ -352,24 +365,18 @@ resstack_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncwarp();
         if (lane == 0) {
-          if (p.has_raw) tma_store_4d(mO, stg + k * 4096, c * 32, t.p0 + r0, 0, t.b);
+          if (p.has_raw) tma_store_4d(mO, stg + slot * 4096, c * 32, t.p0 + r0, 0, t.b);
           if (p.has_act) tma_store_4d(mT, at_base + k * 2048, c * 32, t.p0 + r0, 0, t.b);
           asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-          asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");    // buffers k^1 are free again
-          // residual of this warp's next chunk (this tile's second chunk, or the first of the next tile) -> buffer k^1
-          PTile tn = t; int cn = c + 1; bool more = true;
-          if (cn == 2) {
-            cn = 0;
-            more = i + 1 < n_my;
-            if (more) tn = it.coord();
-          }
-          if (more) {
-            mbar_expect_tx(&rfull[k ^ 1], 4096);
-            tma_load_4d(&tmR, &rfull[k ^ 1], stg + (k ^ 1) * 4096, cn * 32, tn.p0 + r0, 0, tn.b);
+          asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");    // the stores of chunk n-1 have left their buffers
+          if (pn < n_chunks) {                                              // residual of chunk n+3 -> the slot chunk n-1 used
+            const PTile tp = pit.coord();
+            mbar_expect_tx(&rfull[pn & 3], 4096);
+            tma_load_4d(&tmR, &rfull[pn & 3], stg + (pn & 3) * 4096, (int)(pn & 1) * 32, tp.p0 + r0, 0, tp.b);
           }
         }
+        if (pn < n_chunks) { if (pn & 1) pit.next(p); ++pn; }                // warp-uniform bookkeeping of the prefetch stream
         __syncwarp();
-        k ^= 1;
       }
       tc_fence_before();
       mbar_arrive(&acc2_empty[i & (PNACC - 1)]);
@@ -409,7 +416,7 @@ int resstack_pair_tc(const vfx_pair_desc& d, cudaStream_t st) {
   p.bias1 = d.b1; p.bias2 = d.b2;
   p.has_raw = d.write_raw ? 1u : 0u; p.has_act = d.out_act ? 1u : 0u;
   p.act_param = d.act_param;
-  p.epi_warp_bytes = 8192u + (d.out_act ? 4096u : 0u);
+  p.epi_warp_bytes = 16384u + (d.out_act ? 4096u : 0u);
   // c = F32, a = b = BF16, K-major, N = 64, M = 128
   p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(PC >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
   static const bool allow_halo = getenv("VFX_NO_HALO") == nullptr;

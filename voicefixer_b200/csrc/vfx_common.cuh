@@ -56,6 +56,16 @@ __device__ __forceinline__ float round_tf32(float v) {
 __device__ __forceinline__ float to_f(tf32_t v) { return v.v; }
 template <> __device__ __forceinline__ tf32_t from_f<tf32_t>(float v) { return tf32_t{round_tf32(v)}; }
 
+// Encoded tf32 stream (vfx_conv_desc.res_enc / raw_enc): S = bits(lrelu(x)) + 0x1000 -- see include/vfx_b200.h.
+__device__ __forceinline__ float stream_enc(float x, float slope) {
+  const float y = x > 0.f ? x : x * slope;
+  return __uint_as_float(__float_as_uint(y) + 0x1000u);
+}
+__device__ __forceinline__ float stream_dec(float s, float inv_slope) {
+  const float y = __uint_as_float(__float_as_uint(s) - 0x1000u);
+  return y > 0.f ? y : y * inv_slope;
+}
+
 // element size of a GEMM operand / weight in the given vfx_precision
 static inline size_t prec_esz(int precision) { return precision == VFX_PREC_BF16 ? 2 : 4; }
 
