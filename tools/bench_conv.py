@@ -14,6 +14,7 @@ ap.add_argument("--impl", type=int, default=1)
 ap.add_argument("--kind", default="both")
 ap.add_argument("--taps", type=int, default=3)
 ap.add_argument("--dil", type=int, default=3)
+ap.add_argument("--prec", default="bf16")
 args = ap.parse_args()
 dev = "cuda:0"
 shapes = [(512, 7042), (256, 49294), (128, 147882), (64, 443646)]
@@ -21,11 +22,12 @@ for C, L in shapes:
     if args.only and C != args.only:
         continue
     B = args.B
-    a = (torch.randn(B, 1, L, C, device=dev) * 0.5).bfloat16()
-    w = (torch.randn(3, C, C, device=dev) * 0.05).bfloat16()
+    odt = torch.bfloat16 if args.prec == "bf16" else torch.float32
+    a = (torch.randn(B, 1, L, C, device=dev) * 0.5).to(odt)
+    w = (torch.randn(3, C, C, device=dev) * 0.05).to(odt)
     bias = torch.randn(C, device=dev)
     X = torch.randn(B, 1, L, C, device=dev)
-    out_act = torch.empty(B, 1, L, C, device=dev, dtype=torch.bfloat16)
+    out_act = torch.empty(B, 1, L, C, device=dev, dtype=odt)
     for kind in ("c1", "c2", "raw", "rawact", "actnone"):
         if (args.kind == "both" and kind not in ("c1", "c2")) or args.kind not in ("both", "all", kind):
             continue
@@ -33,17 +35,17 @@ for C, L in shapes:
             taps1 = [(0, -args.dil), (0, 0), (0, args.dil)][:args.taps] if args.taps < 3 else [(0, -args.dil), (0, 0), (0, args.dil)]
             if kind == "c1":
                 conv_gemm(a, w, taps1, bias=bias, want_raw=False, want_act=True, act="lrelu",
-                          act_param=0.01, precision="bf16", impl=args.impl, out_act=out_act)
+                          act_param=0.01, precision=args.prec, impl=args.impl, out_act=out_act)
             elif kind == "c2":
                 conv_gemm(a, w, [(0, -1), (0, 0), (0, 1)], bias=bias, residual=X, want_raw=True, want_act=True,
-                          act="lrelu", act_param=0.01, precision="bf16", impl=args.impl, out_raw=X, out_act=out_act)
+                          act="lrelu", act_param=0.01, precision=args.prec, impl=args.impl, out_raw=X, out_act=out_act)
             elif kind == "raw":
-                conv_gemm(a, w, taps1, bias=bias, want_raw=True, want_act=False, precision="bf16", impl=args.impl, out_raw=X)
+                conv_gemm(a, w, taps1, bias=bias, want_raw=True, want_act=False, precision=args.prec, impl=args.impl, out_raw=X)
             elif kind == "rawact":
                 conv_gemm(a, w, taps1, bias=bias, want_raw=True, want_act=True, act="lrelu", act_param=0.01,
-                          precision="bf16", impl=args.impl, out_raw=X, out_act=out_act)
+                          precision=args.prec, impl=args.impl, out_raw=X, out_act=out_act)
             elif kind == "actnone":
-                conv_gemm(a, w, taps1, bias=bias, want_raw=False, want_act=True, act="none", precision="bf16",
+                conv_gemm(a, w, taps1, bias=bias, want_raw=False, want_act=True, act="none", precision=args.prec,
                           impl=args.impl, out_act=out_act)
         run()
         torch.cuda.synchronize()
@@ -54,5 +56,6 @@ for C, L in shapes:
         e1.record(); torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / args.iters
         flops = 2.0 * 3 * C * C * L * B
-        byts = B * L * C * {"c1": 4, "c2": 12, "raw": 6, "rawact": 8, "actnone": 4}[kind]
+        e = 2 if args.prec == "bf16" else 4
+        byts = B * L * C * {"c1": 2 * e, "c2": 2 * e + 8, "raw": e + 4, "rawact": 2 * e + 4, "actnone": 2 * e}[kind]
         print(f"C={C:4d} L={L:7d} B={B} {kind}: {ms:8.3f} ms  {flops/ms/1e9:8.1f} TF/s  {byts/ms/1e6:8.1f} GB/s (algorithmic)", flush=True)

@@ -28,11 +28,16 @@ template <> struct Vec8<float> {
     v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
   }
 };
+// tf32 operands: what kind::tf32 does with an fp32 word -- the low 13 mantissa bits are ignored (measured on B200,
+// tools/probe_tf32_rounding.py).  Pre-rounded operands pass through unchanged; an encoded stream (res_enc / raw_enc)
+// comes out as round-to-nearest(lrelu(x)), exactly as on the tensor core.
 template <> struct Vec8<tf32_t> {
   float v[8];
   __device__ void load(const tf32_t* p) {
-    float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
-    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+    const uint4 a = *reinterpret_cast<const uint4*>(p), b = *reinterpret_cast<const uint4*>(p + 4);
+    const uint32_t u[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(u[i] & 0xFFFFE000u);
   }
 };
 template <> struct Vec8<__nv_bfloat16> {

@@ -41,7 +41,7 @@ struct vfx_engine {
   float2* d_tw = nullptr;       // exp(-2 pi i k / 2048), k < 1024
   std::vector<std::string> missing;
   int parts = 0;    // VFX_PART_* bits of the weight sets found complete by vfx_engine_finalize
-  int tf32_stream = 0;  // TF32: vocoder residual streams are kept as ONE encoded fp32 tensor (operand + residual carrier)
+  int tf32_stream = 1;  // TF32: vocoder residual streams are kept as ONE encoded fp32 tensor (operand + residual carrier)
   int fuse_pair = 1;  // BF16: ResStack pairs of width 64 run as ONE fused kernel (resstack_pair_tc.cu)
   int profile = 0;
   std::vector<vfx::ProfRec> prof;

@@ -53,7 +53,7 @@ __device__ __forceinline__ float round_tf32(float v) {
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v));
   return __uint_as_float(u);
 }
-__device__ __forceinline__ float to_f(tf32_t v) { return v.v; }
+__device__ __forceinline__ float to_f(tf32_t v) { return __uint_as_float(__float_as_uint(v.v) & 0xFFFFE000u); }   // as the tensor core reads it
 template <> __device__ __forceinline__ tf32_t from_f<tf32_t>(float v) { return tf32_t{round_tf32(v)}; }
 
 // Encoded tf32 stream (vfx_conv_desc.res_enc / raw_enc): S = bits(lrelu(x)) + 0x1000 -- see include/vfx_b200.h.
