@@ -84,6 +84,8 @@ struct TcParams {
                             // [(128+2d) rows], or 3x3 [(th+2) x tw rows starting at (w0-1, h0-1)]
   uint32_t halo_boxes;                 // 1 = one halo box per K chunk; ntaps = one 128-row box per tap (multi-box tile stage)
   uint32_t halo_rows, halo_kc_bytes;   // rows of the TMA box, bytes of one K-chunk block (rows rounded up + zero pad rows)
+  uint32_t halo_nps;                   // K chunks per pipeline stage in halo mode: n_kc (a tile = one stage), or 1 when only
+                                       // single-chunk stages leave room for two of them (tf32 C = 64 with three tap boxes)
   int halo_pw, halo_ph;                // the box starts at (w0 - pw, h0 - ph)
   uint32_t halo_off[9];                // row offset of each tap's 128-row view inside the box
   uint32_t jtiles;          // tiles whose k-steps are interleaved (independent accumulators hide MMA latency)
@@ -125,7 +127,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   // [resident weights | S stages of (A [+ W]) | epilogue staging (TMA epilogue) | barriers]
   uint8_t* wres = smem;
   smem += p.w_bytes;
-  const uint32_t stage_bytes = p.halo ? p.halo_kc_bytes * (uint32_t)p.n_kc : p.a_stage_bytes + (p.w_resident ? 0u : p.b_stage_bytes);
+  const uint32_t stage_bytes = p.halo ? p.halo_kc_bytes * p.halo_nps : p.a_stage_bytes + (p.w_resident ? 0u : p.b_stage_bytes);
   uint8_t* staging = smem + (size_t)p.stages * stage_bytes;
   float* bias_s = reinterpret_cast<float*>(staging + (p.tma_epi ? p.epi_warps * p.epi_warp_bytes : 0));
   float* asc_s = bias_s + p.bias_floats;                // act_scale / act_shift copies (TMA epilogue)
@@ -162,7 +164,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
   if (p.halo) {   // rows behind the TMA box (read by the last taps' views, never written by TMA) must be zero
     const uint32_t row_b = p.row_bytes, used = p.halo_rows * row_b, blk = p.halo_kc_bytes;
-    const uint32_t nblk = (uint32_t)p.stages * (uint32_t)p.n_kc, padw = (blk - used) / 4;
+    const uint32_t nblk = (uint32_t)p.stages * p.halo_nps, padw = (blk - used) / 4;
     if (padw)
       for (uint32_t i = threadIdx.x; i < nblk * padw; i += NUM_THREADS)
         reinterpret_cast<uint32_t*>(smem + (size_t)(i / padw) * blk + used)[i % padw] = 0u;
@@ -199,24 +201,28 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         for (uint32_t i = 0; i < n_my; ++i) {
           const TileCoord t = pit.coord(p);
           pit.next(p);
-          mbar_wait_t(&empty[s], ph ^ 1, w_empty, dbg);
-          uint8_t* sa = smem + (size_t)s * stage_bytes;
-          if (elect_one()) {
-            mbar_expect_tx(&full[s], p.halo_rows * p.row_bytes * (uint32_t)p.n_kc * p.halo_boxes);
 #pragma unroll 1
-            for (int kc = 0; kc < p.n_kc; ++kc) {
-              if (p.halo_boxes == 1) {
-                tma_load_4d(&tmA, &full[s], sa + (size_t)kc * p.halo_kc_bytes, kc * p.KC, t.w0 - p.halo_pw, t.h0 - p.halo_ph, t.b);
-              } else {      // one aligned 128-row box per tap, all on this stage's barrier
+          for (int kc0 = 0; kc0 < p.n_kc; kc0 += (int)p.halo_nps) {
+            mbar_wait_t(&empty[s], ph ^ 1, w_empty, dbg);
+            uint8_t* sa = smem + (size_t)s * stage_bytes;
+            if (elect_one()) {
+              mbar_expect_tx(&full[s], p.halo_rows * p.row_bytes * p.halo_nps * p.halo_boxes);
 #pragma unroll 1
-                for (int tap = 0; tap < p.ntaps; ++tap)
-                  tma_load_4d(&tmA, &full[s], sa + (size_t)kc * p.halo_kc_bytes + (size_t)p.halo_off[tap] * p.row_bytes, kc * p.KC,
-                              t.w0 + p.dw[tap], t.h0 + p.dh[tap], t.b);
+              for (int kc = kc0; kc < kc0 + (int)p.halo_nps; ++kc) {
+                uint8_t* const blk = sa + (size_t)(kc - kc0) * p.halo_kc_bytes;
+                if (p.halo_boxes == 1) {
+                  tma_load_4d(&tmA, &full[s], blk, kc * p.KC, t.w0 - p.halo_pw, t.h0 - p.halo_ph, t.b);
+                } else {      // one aligned 128-row box per tap, all on this stage's barrier
+#pragma unroll 1
+                  for (int tap = 0; tap < p.ntaps; ++tap)
+                    tma_load_4d(&tmA, &full[s], blk + (size_t)p.halo_off[tap] * p.row_bytes, kc * p.KC,
+                                t.w0 + p.dw[tap], t.h0 + p.dh[tap], t.b);
+                }
               }
             }
+            __syncwarp();
+            if (++s == (uint32_t)p.stages) { s = 0; ph ^= 1; }
           }
-          __syncwarp();
-          if (++s == (uint32_t)p.stages) { s = 0; ph ^= 1; }
         }
         n_done = n_my;
       }
@@ -265,49 +271,52 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       if (p.halo) {
         for (uint32_t i = 0; i < n_my; ++i) {
           mbar_wait_t(&tmem_empty[i & nacc_mask], ((i >> nacc_log2) & 1) ^ 1, w_te, dbg);
-          mbar_wait_t(&full[s], ph, w_full, dbg);
-          tc_fence_after();
           const uint32_t d_tmem = tmem_base + (i & nacc_mask) * p.Ntile;
-          const uint32_t s_addr = smem_u32(smem + (size_t)s * stage_bytes);
           const uint32_t w_addr = smem_u32(wres);
           const uint32_t dhi = desc_hi(p.sbo16, p.layout_type);
-          if (elect_one()) {
-            // ntaps is 3 (1-D) or 9 (3x3): bodies of 3 taps x kk MMAs are unrolled so that the descriptor
-            // arithmetic and the moves into uniform registers of several MMAs overlap (a fully rolled loop
-            // serialised ~200 cycles per MMA and made this warp the bottleneck of the N=32 UNet layers)
 #pragma unroll 1
-            for (int tap0 = 0; tap0 < p.ntaps; tap0 += 3) {
+          for (int kc0 = 0; kc0 < p.n_kc; kc0 += (int)p.halo_nps) {
+            mbar_wait_t(&full[s], ph, w_full, dbg);
+            tc_fence_after();
+            const uint32_t s_addr = smem_u32(smem + (size_t)s * stage_bytes);
+            if (elect_one()) {
+              // ntaps is 3 (1-D) or 9 (3x3): bodies of 3 taps x kk MMAs are unrolled so that the descriptor
+              // arithmetic and the moves into uniform registers of several MMAs overlap (a fully rolled loop
+              // serialised ~200 cycles per MMA and made this warp the bottleneck of the N=32 UNet layers)
 #pragma unroll 1
-              for (int kc = 0; kc < p.n_kc; ++kc) {
-                uint32_t a_lo[3], b_lo[3];
+              for (int tap0 = 0; tap0 < p.ntaps; tap0 += 3) {
+#pragma unroll 1
+                for (int kc = kc0; kc < kc0 + (int)p.halo_nps; ++kc) {
+                  uint32_t a_lo[3], b_lo[3];
 #pragma unroll
-                for (int dt = 0; dt < 3; ++dt) {
-                  a_lo[dt] = desc_lo(s_addr + (uint32_t)kc * p.halo_kc_bytes + p.halo_off[tap0 + dt] * p.row_bytes);
-                  b_lo[dt] = desc_lo(w_addr + (uint32_t)((tap0 + dt) * p.n_kc + kc) * p.b_stage_bytes);
-                }
-                if ((tap0 | kc) == 0) tc_mma_lo<false, TF32>(d_tmem, a_lo[0], b_lo[0], dhi, p.idesc);   // first MMA of the tile overwrites
-                else tc_mma_lo<true, TF32>(d_tmem, a_lo[0], b_lo[0], dhi, p.idesc);
-                if (kk == 4) {
+                  for (int dt = 0; dt < 3; ++dt) {
+                    a_lo[dt] = desc_lo(s_addr + (uint32_t)(kc - kc0) * p.halo_kc_bytes + p.halo_off[tap0 + dt] * p.row_bytes);
+                    b_lo[dt] = desc_lo(w_addr + (uint32_t)((tap0 + dt) * p.n_kc + kc) * p.b_stage_bytes);
+                  }
+                  if ((tap0 | kc) == 0) tc_mma_lo<false, TF32>(d_tmem, a_lo[0], b_lo[0], dhi, p.idesc);   // first MMA of the tile overwrites
+                  else tc_mma_lo<true, TF32>(d_tmem, a_lo[0], b_lo[0], dhi, p.idesc);
+                  if (kk == 4) {
 #pragma unroll
-                  for (int k = 1; k < 4; ++k) tc_mma_lo<true, TF32>(d_tmem, a_lo[0] + 2 * k, b_lo[0] + 2 * k, dhi, p.idesc);
+                    for (int k = 1; k < 4; ++k) tc_mma_lo<true, TF32>(d_tmem, a_lo[0] + 2 * k, b_lo[0] + 2 * k, dhi, p.idesc);
 #pragma unroll
-                  for (int dt = 1; dt < 3; ++dt)
+                    for (int dt = 1; dt < 3; ++dt)
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) tc_mma_lo<true, TF32>(d_tmem, a_lo[dt] + 2 * k, b_lo[dt] + 2 * k, dhi, p.idesc);
-                } else {
-                  tc_mma_lo<true, TF32>(d_tmem, a_lo[0] + 2, b_lo[0] + 2, dhi, p.idesc);
+                      for (int k = 0; k < 4; ++k) tc_mma_lo<true, TF32>(d_tmem, a_lo[dt] + 2 * k, b_lo[dt] + 2 * k, dhi, p.idesc);
+                  } else {
+                    tc_mma_lo<true, TF32>(d_tmem, a_lo[0] + 2, b_lo[0] + 2, dhi, p.idesc);
 #pragma unroll
-                  for (int dt = 1; dt < 3; ++dt)
+                    for (int dt = 1; dt < 3; ++dt)
 #pragma unroll
-                    for (int k = 0; k < 2; ++k) tc_mma_lo<true, TF32>(d_tmem, a_lo[dt] + 2 * k, b_lo[dt] + 2 * k, dhi, p.idesc);
+                      for (int k = 0; k < 2; ++k) tc_mma_lo<true, TF32>(d_tmem, a_lo[dt] + 2 * k, b_lo[dt] + 2 * k, dhi, p.idesc);
+                  }
                 }
               }
+              tc_commit(&empty[s]);
+              if (kc0 + (int)p.halo_nps >= p.n_kc) tc_commit(&tmem_full[i & nacc_mask]);
             }
-            tc_commit(&empty[s]);
-            tc_commit(&tmem_full[i & nacc_mask]);
+            __syncwarp();
+            if (++s == (uint32_t)p.stages) { s = 0; ph ^= 1; }
           }
-          __syncwarp();
-          if (++s == (uint32_t)p.stages) { s = 0; ph ^= 1; }
         }
         n_done = n_my;
       }
@@ -732,7 +741,8 @@ int conv_gemm_tc(int precision, const vfx_conv_desc& d, cudaStream_t st) {
     const uint32_t row_b = row_bytes;
     bool ok = false;
     uint32_t box_w = 0, box_h = 0, extra = 0;
-    if (d.H == 1 && d.Hq == 1 && d.ntaps == 3 && tw == TILE_M && row_bytes == 128 && d.dw[1] == 0 && d.dw[2] > 0 && d.dw[2] <= 64 &&
+    static const bool allow_halo_1d = getenv("VFX_NO_HALO_1D") == nullptr;
+    if (allow_halo_1d && d.H == 1 && d.Hq == 1 && d.ntaps == 3 && tw == TILE_M && row_bytes == 128 && d.dw[1] == 0 && d.dw[2] > 0 && d.dw[2] <= 64 &&
         d.dw[0] == -d.dw[2] && d.dh[0] == 0 && d.dh[1] == 0 && d.dh[2] == 0) {
       const int dd = d.dw[2];
       box_w = TILE_M + 2 * dd; box_h = 1; p.halo_pw = dd; p.halo_ph = 0;
@@ -758,12 +768,17 @@ int conv_gemm_tc(int precision, const vfx_conv_desc& d, cudaStream_t st) {
       p.halo_rows = box_w * box_h;
       p.halo_kc_bytes = ((p.halo_rows * p.halo_boxes + extra + 7) / 8) * 8 * row_b;
       p.halo_kc_bytes = (p.halo_kc_bytes + 1023) / 1024 * 1024;
-      // worth it only if at least 2 tiles can be in flight
-      p.halo = ((uint32_t)SMEM_BUDGET - p.w_bytes - epi_smem) / (p.halo_kc_bytes * (uint32_t)p.n_kc) >= 2 ? 1u : 0u;
+      // a stage normally holds all K chunks of a tile; worth it only if at least 2 stages fit.  If they do not, but two
+      // single-chunk stages do (1-D: tf32 C = 64 with three tap boxes, 48 KB per chunk), a tile becomes n_kc stages.
+      const uint32_t room = (uint32_t)SMEM_BUDGET - p.w_bytes - epi_smem;
+      p.halo_nps = (uint32_t)p.n_kc;
+      p.halo = room / (p.halo_kc_bytes * (uint32_t)p.n_kc) >= 2 ? 1u : 0u;
+      if (!p.halo && d.H == 1 && p.n_kc > 1 && room / p.halo_kc_bytes >= 2) { p.halo = 1u; p.halo_nps = 1u; }
       halo_box_w = box_w; halo_box_h = box_h;
     }
   }
-  const uint32_t stage_bytes = p.halo ? p.halo_kc_bytes * (uint32_t)p.n_kc : p.a_stage_bytes + (p.w_resident ? 0u : p.b_stage_bytes);
+  if (!p.halo) p.halo_nps = (uint32_t)p.n_kc;
+  const uint32_t stage_bytes = p.halo ? p.halo_kc_bytes * p.halo_nps : p.a_stage_bytes + (p.w_resident ? 0u : p.b_stage_bytes);
   int stages = (int)((SMEM_BUDGET - p.w_bytes - epi_smem) / stage_bytes);
   if (stages > MAX_STAGES) stages = MAX_STAGES;
   const int k_steps = p.ntaps * p.n_kc;

@@ -16,8 +16,8 @@
 //   h rows whose position lies outside [0, L) are zero (conv2's zero padding applies to h, not to x).
 // * Both weight sets (2 x 3 x [64][64] bf16 = 48 KB) stay resident in shared memory.
 // * Roles (persistent CTA per SM, 320 threads):
-//     warp 0     TMA producer: the a tile -- dilation <= 64: ONE box of 128 + 2d rows per tile, the taps are row-shifted
-//                views of it; larger dilations: one 128-row box per tap, each its own pipeline stage
+//     warp 0     TMA producer: one aligned 128-row box of the operand per tap, each its own pipeline stage (the three
+//                boxes of a tile overlap in L2; a single halo box with row-shifted tap views measured slower, see below)
 //     warp 1     MMA issuer, software-pipelined: conv1(i), then conv2(i-1) while the h tile of i is being produced
 //     warp 2-5   epilogue 1: TMEM -> +b1 -> lrelu -> bf16 -> h tile (double-buffered)
 //     warp 6-9   epilogue 2: TMA-staged like conv_gemm_tc's: residual tiles in by TMA (ring of four, prefetched three
@@ -419,8 +419,11 @@ int resstack_pair_tc(const vfx_pair_desc& d, cudaStream_t st) {
   p.epi_warp_bytes = 16384u + (d.out_act ? 4096u : 0u);
   // c = F32, a = b = BF16, K-major, N = 64, M = 128
   p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(PC >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-  static const bool allow_halo = getenv("VFX_NO_HALO") == nullptr;
-  p.halo = (allow_halo && d.dilation <= 64) ? 1u : 0u;
+  // One box per tap by default: measured on B200 (tools/bench_pair.py, B = 32) the single halo box with row-shifted tap
+  // views is SLOWER than three aligned 128-row boxes -- d = 1: 1.84 vs 1.72 ms, d = 27: 1.89 vs 1.68 ms (the L2 absorbs
+  // the 3x operand re-reads; every MMA of conv1 then reads an 8-row-aligned tile).  VFX_PAIR_HALO=1 selects the halo box.
+  static const bool want_halo = getenv("VFX_PAIR_HALO") != nullptr;
+  p.halo = (want_halo && d.dilation <= 64) ? 1u : 0u;
   p.halo_rows = 128u + 2u * (uint32_t)d.dilation;
   p.stage_bytes = p.halo ? ((p.halo_rows + 2u) * 128u + 1023u) / 1024u * 1024u : 128u * 128u;
   const uint32_t fixed = 2u * PW_BYTES + 2u * PH_BYTES + 4u * p.epi_warp_bytes + 2u * PC * 4u + 1024u /*align*/ + 512u /*barriers*/;
