@@ -301,12 +301,13 @@ def wl_cli(precision, n_files=8, seconds=10.0):
             "jobs_wall_s": jobs_wall, "value": (n_files * seconds / jobs_wall) if jobs_wall else None, "unit": UNIT}
 
 
-def csrc_sha():
-    """Hash of the CUDA sources: an ncu traffic figure is only quoted when it was captured from these sources."""
+def csrc_sha(files=None):
+    """Hash of CUDA sources (all of csrc/, or the listed files): an ncu traffic figure is only quoted when the kernel it was
+    captured from is built from the same sources as the one that just ran."""
     import hashlib
     h = hashlib.sha256()
     d = os.path.join(ROOT, "voicefixer_b200", "csrc")
-    for f in sorted(os.listdir(d)):
+    for f in sorted(files or os.listdir(d)):
         h.update(open(os.path.join(d, f), "rb").read())
     return h.hexdigest()[:16]
 
@@ -342,7 +343,7 @@ def roofline_from(rep, B, L_by_stack, precision, peaks, peaks_src, tot_ms):
     if os.path.exists(tpath):
         tj = json.load(open(tpath))
         ent = tj.get(f"{precision}:voc.rs{dom['j']}.pair:B{B}")
-        if ent and ent.get("csrc_sha") == csrc_sha():
+        if ent and ent.get("csrc_sha") == csrc_sha(ent.get("files")):
             traffic, tnote = ent["dram_bytes_per_pair"], ent.get("source", "profiles/")
         elif ent:
             tnote = "capture in profiles/ncu_traffic.json is from older sources: not quoted"

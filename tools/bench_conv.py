@@ -28,8 +28,11 @@ for C, L in shapes:
     bias = torch.randn(C, device=dev)
     X = torch.randn(B, 1, L, C, device=dev)
     out_act = torch.empty(B, 1, L, C, device=dev, dtype=odt)
-    for kind in ("c1", "c2", "raw", "rawact", "actnone"):
-        if (args.kind == "both" and kind not in ("c1", "c2")) or args.kind not in ("both", "all", kind):
+    for kind in ("c1", "c2", "c2enc", "raw", "rawact", "actnone"):
+        if args.kind == "pairenc":
+            if kind not in ("c1", "c2enc"):
+                continue
+        elif (args.kind == "both" and kind not in ("c1", "c2")) or args.kind not in ("both", "all", kind):
             continue
         def run():
             taps1 = [(0, -args.dil), (0, 0), (0, args.dil)][:args.taps] if args.taps < 3 else [(0, -args.dil), (0, 0), (0, args.dil)]
@@ -39,6 +42,9 @@ for C, L in shapes:
             elif kind == "c2":
                 conv_gemm(a, w, [(0, -1), (0, 0), (0, 1)], bias=bias, residual=X, want_raw=True, want_act=True,
                           act="lrelu", act_param=0.01, precision=args.prec, impl=args.impl, out_raw=X, out_act=out_act)
+            elif kind == "c2enc":     # tf32 encoded stream: residual decoded, result encoded in place, no separate operand copy
+                conv_gemm(a, w, [(0, -1), (0, 0), (0, 1)], bias=bias, residual=X, want_raw=True, want_act=False,
+                          precision=args.prec, impl=args.impl, out_raw=X, res_enc=1, raw_enc=1, enc_slope=0.01)
             elif kind == "raw":
                 conv_gemm(a, w, taps1, bias=bias, want_raw=True, want_act=False, precision=args.prec, impl=args.impl, out_raw=X)
             elif kind == "rawact":
@@ -57,5 +63,5 @@ for C, L in shapes:
         ms = e0.elapsed_time(e1) / args.iters
         flops = 2.0 * 3 * C * C * L * B
         e = 2 if args.prec == "bf16" else 4
-        byts = B * L * C * {"c1": 2 * e, "c2": 2 * e + 8, "raw": e + 4, "rawact": 2 * e + 4, "actnone": 2 * e}[kind]
+        byts = B * L * C * {"c1": 2 * e, "c2": 2 * e + 8, "c2enc": e + 8, "raw": e + 4, "rawact": 2 * e + 4, "actnone": 2 * e}[kind]
         print(f"C={C:4d} L={L:7d} B={B} {kind}: {ms:8.3f} ms  {flops/ms/1e9:8.1f} TF/s  {byts/ms/1e6:8.1f} GB/s (algorithmic)", flush=True)

@@ -769,11 +769,12 @@ int conv_gemm_tc(int precision, const vfx_conv_desc& d, cudaStream_t st) {
       p.halo_kc_bytes = ((p.halo_rows * p.halo_boxes + extra + 7) / 8) * 8 * row_b;
       p.halo_kc_bytes = (p.halo_kc_bytes + 1023) / 1024 * 1024;
       // a stage normally holds all K chunks of a tile; worth it only if at least 2 stages fit.  If they do not, but two
-      // single-chunk stages do (1-D: tf32 C = 64 with three tap boxes, 48 KB per chunk), a tile becomes n_kc stages.
+      // single-chunk stages do (tf32: C = 64 ResStack conv with three tap boxes, 48 KB per chunk; the 64 -> 32 3x3 conv of the
+      // UNet's last decoder level, 50 KB per chunk), a tile becomes n_kc stages.
       const uint32_t room = (uint32_t)SMEM_BUDGET - p.w_bytes - epi_smem;
       p.halo_nps = (uint32_t)p.n_kc;
       p.halo = room / (p.halo_kc_bytes * (uint32_t)p.n_kc) >= 2 ? 1u : 0u;
-      if (!p.halo && d.H == 1 && p.n_kc > 1 && room / p.halo_kc_bytes >= 2) { p.halo = 1u; p.halo_nps = 1u; }
+      if (!p.halo && p.n_kc > 1 && room / p.halo_kc_bytes >= 2) { p.halo = 1u; p.halo_nps = 1u; }
       halo_box_w = box_w; halo_box_h = box_h;
     }
   }

@@ -21,6 +21,7 @@
 //   * fp32 FMA throughout (the recurrence is precision-sensitive); gi for step t+1 is prefetched
 //     into registers during step t.
 #include <cooperative_groups.h>
+#include <stdlib.h>
 #include "vfx_common.cuh"
 
 namespace cg = cooperative_groups;
@@ -33,14 +34,16 @@ constexpr int H = 256, G3 = 768;
 constexpr int CL = 8;            // CTAs per cluster
 constexpr int UPC = H / CL;      // hidden units per CTA = 32
 constexpr int RPC = 3 * UPC;     // gate rows per CTA = 96
-constexpr int KQ = 8;            // K split: one 32-wide slice per warp
-constexpr int KW = H / KQ;       // 32
-constexpr int NT = 32 * KQ;      // 256 threads: lane = hidden unit of this CTA, warp = K slice
+// K split: one H/KQ-wide slice per warp, KQ warps per CTA (lane = hidden unit of this CTA, warp = K slice).
+// KQ = 8 (default): 256 threads x 96 weights; KQ = 16 (VFX_GRU_KQ=16): 512 threads x 48 weights -- same total work, twice
+// the warps.  An ncu capture of KQ = 8 shows 25 % issue-active and 24 % of samples in the mbarrier wait of the exchange;
+// doubling the warps did not shorten the step (see gru_layer below), so the default stays at 8.
 
-template <int G>
-__global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(NT, 1)
+template <int G, int KQ>
+__global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(32 * KQ, 1)
 gru_cluster_kernel(const float* __restrict__ gi, const float* __restrict__ whh_t,
                    const float* __restrict__ bhh, int B, int T, float* __restrict__ out) {
+  constexpr int KW = H / KQ, NT = 32 * KQ;
   extern __shared__ __align__(16) uint8_t gru_smem[];
   float (*h_s)[G][H] = reinterpret_cast<float (*)[G][H]>(gru_smem);                       // [2][G][H]
   float (*part)[KQ][G][RPC] = reinterpret_cast<float (*)[KQ][G][RPC]>(gru_smem + sizeof(float) * 2 * G * H);
@@ -182,18 +185,19 @@ gru_cluster_kernel(const float* __restrict__ gi, const float* __restrict__ whh_t
   cluster.sync();   // no CTA may exit while a peer could still address its shared memory
 }
 
-template <int G>
+template <int G, int KQ>
 int launch(const float* gi, const float* whh_t, const float* bhh, int B, int T, float* out, cudaStream_t st) {
+  constexpr int NT = 32 * KQ;
   const int groups = (B + G - 1) / G;
   const size_t smem = sizeof(float) * (2 * G * H + 2 * KQ * G * RPC) + 16;
   static bool attr_set[64] = {false};           // per device: the attribute belongs to the device's copy of the function
   int dev = 0;
   VFX_CUDA_CHECK(cudaGetDevice(&dev));
   if (dev >= 64 || !attr_set[dev]) {
-    VFX_CUDA_CHECK(cudaFuncSetAttribute(gru_cluster_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    VFX_CUDA_CHECK(cudaFuncSetAttribute(gru_cluster_kernel<G, KQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     if (dev < 64) attr_set[dev] = true;
   }
-  gru_cluster_kernel<G><<<2 * groups * CL, NT, smem, st>>>(gi, whh_t, bhh, B, T, out);
+  gru_cluster_kernel<G, KQ><<<2 * groups * CL, NT, smem, st>>>(gi, whh_t, bhh, B, T, out);
   VFX_LAUNCH_CHECK();
   return VFX_OK;
 }
@@ -204,9 +208,17 @@ int gru_layer(const float* gi, const float* whh_t, const float* bhh, int B, int 
               cudaStream_t st) {
   VFX_REQUIRE(B > 0 && T > 0, "gru_layer: empty problem");
   // one wave: 8 GPCs x 2 clusters of 8 CTAs = 16 co-resident clusters on the 148 SMs
-  if (2 * ((B + 1) / 2) <= 16) return launch<2>(gi, whh_t, bhh, B, T, out, st);
-  if (2 * ((B + 3) / 4) <= 16) return launch<4>(gi, whh_t, bhh, B, T, out, st);
-  return launch<8>(gi, whh_t, bhh, B, T, out, st);
+  // measured on B200 (B = 32, T = 1001, four layers per step): KQ = 8: 8.8 / 11.0 ms, KQ = 16: 9.9 / 9.7 ms in two runs each --
+  // within run-to-run noise, step time unchanged (88.9 vs 89.1 ms): the step is bound by the serial chain, not by warp count
+  static const int kq = getenv("VFX_GRU_KQ") ? atoi(getenv("VFX_GRU_KQ")) : 8;
+  if (kq == 8) {
+    if (2 * ((B + 1) / 2) <= 16) return launch<2, 8>(gi, whh_t, bhh, B, T, out, st);
+    if (2 * ((B + 3) / 4) <= 16) return launch<4, 8>(gi, whh_t, bhh, B, T, out, st);
+    return launch<8, 8>(gi, whh_t, bhh, B, T, out, st);
+  }
+  if (2 * ((B + 1) / 2) <= 16) return launch<2, 16>(gi, whh_t, bhh, B, T, out, st);
+  if (2 * ((B + 3) / 4) <= 16) return launch<4, 16>(gi, whh_t, bhh, B, T, out, st);
+  return launch<8, 16>(gi, whh_t, bhh, B, T, out, st);
 }
 
 }  // namespace vfx
