@@ -41,8 +41,9 @@ namespace vfx {
 namespace {
 
 constexpr int TILE_M = 128;
-constexpr int NUM_EPI_WARPS = 8;          // two per TMEM sub-partition, interleaved over column chunks
-constexpr int NUM_THREADS = 64 + 32 * NUM_EPI_WARPS;
+constexpr int MAX_EPI_WARPS = 8;          // launch-time choice (TcParams.epi_warps): 4 = one per TMEM sub-partition (default),
+                                          // 8 = two per sub-partition, interleaved over even / odd column chunks
+constexpr int NUM_THREADS = 64 + 32 * MAX_EPI_WARPS;     // upper bound (launch bounds); the launch uses 64 + 32 * epi_warps
 constexpr int SMEM_BUDGET = 216 * 1024;                   // weights + stages + epilogue staging (227 KB max incl. barriers/alignment)
 constexpr int MAX_STAGES = 24;
 constexpr int BIAS_SMEM_FLOATS = 2048;                   // TMA epilogue: max N whose bias / affine arrays are kept in smem
@@ -67,7 +68,9 @@ struct TcParams {
   uint32_t at_bytes;        // TMA epilogue: bytes of one activated-operand staging tile (32 rows x 32 columns)
   uint32_t res_enc, raw_enc;           // encoded tf32 stream (vfx_conv_desc): decode the residual / encode the raw output
   float enc_slope, enc_inv_slope;
-  uint32_t epi_warps;       // TMA epilogue: warps that own staging (4 when the tile has one 32-column chunk: the odd-chunk warps idle)
+  uint32_t epi_warps;       // epilogue warps: 4 or 8 (the column chunks of a tile are dealt round-robin over epi_warps / 4 warps)
+  uint32_t stag_warps;      // ... of which own TMA-epilogue staging (8 warps at Ntile = 32: the odd-chunk warps idle)
+  uint32_t ro_slots;        // TMA epilogue: residual / raw staging ring per warp (2 or 4 tiles of 4 KB), prefetched ro_slots - 1 chunks ahead
   uint32_t at_double;       // ... double-buffered (bf16) or single (tf32: see the wait before it is rewritten)
   uint32_t sbo16;           // stride-byte-offset >> 4 of the K-major swizzled layout (8 rows)
   uint32_t layout_type;     // 2 = SWIZZLE_128B, 4 = SWIZZLE_64B
@@ -111,7 +114,6 @@ struct TileIter {
     ih += p.d_ih + c; c = ih >= p.n_th; ih -= c ? p.n_th : 0;
     b += p.d_b + c;
   }
-  __device__ __forceinline__ bool valid(const TcParams& p) const { return b < p.B; }
   __device__ __forceinline__ TileCoord coord(const TcParams& p) const {
     TileCoord t; t.b = b; t.h0 = ih * p.th; t.w0 = iw << p.tw_log2; t.n0 = nt * p.Ntile; return t;
   }
@@ -129,7 +131,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   smem += p.w_bytes;
   const uint32_t stage_bytes = p.halo ? p.halo_kc_bytes * p.halo_nps : p.a_stage_bytes + (p.w_resident ? 0u : p.b_stage_bytes);
   uint8_t* staging = smem + (size_t)p.stages * stage_bytes;
-  float* bias_s = reinterpret_cast<float*>(staging + (p.tma_epi ? p.epi_warps * p.epi_warp_bytes : 0));
+  float* bias_s = reinterpret_cast<float*>(staging + (p.tma_epi ? p.stag_warps * p.epi_warp_bytes : 0));
   float* asc_s = bias_s + p.bias_floats;                // act_scale / act_shift copies (TMA epilogue)
   float* ash_s = asc_s + p.bias_floats;
   uint64_t* bars = reinterpret_cast<uint64_t*>(bias_s + (p.tma_epi ? 3 * p.bias_floats : 0));
@@ -138,7 +140,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   uint64_t* tmem_full = bars + 2 * p.stages;
   uint64_t* tmem_empty = tmem_full + 8;
   uint64_t* wfull = tmem_empty + 8;
-  uint64_t* res_full = wfull + 1;                       // [8 warps][2 buffers]
+  uint64_t* res_full = wfull + 1;                       // [epilogue warp][ring slot]: 8 x 2 or 4 x 4
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_full + 16);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -157,7 +159,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   if (p.tma_epi)
-    for (int i = threadIdx.x; i < p.N; i += NUM_THREADS) {
+    for (int i = threadIdx.x; i < p.N; i += blockDim.x) {
       bias_s[i] = p.bias ? p.bias[i % p.bias_mod] : 0.f;
       asc_s[i] = p.act_scale ? p.act_scale[i] : 1.f;
       ash_s[i] = p.act_scale ? p.act_shift[i] : 0.f;
@@ -166,7 +168,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const uint32_t row_b = p.row_bytes, used = p.halo_rows * row_b, blk = p.halo_kc_bytes;
     const uint32_t nblk = (uint32_t)p.stages * p.halo_nps, padw = (blk - used) / 4;
     if (padw)
-      for (uint32_t i = threadIdx.x; i < nblk * padw; i += NUM_THREADS)
+      for (uint32_t i = threadIdx.x; i < nblk * padw; i += blockDim.x)
         reinterpret_cast<uint32_t*>(smem + (size_t)(i / padw) * blk + used)[i % padw] = 0u;
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
@@ -357,27 +359,41 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       if (dbg && lane == 0) { long long* o = p.dbg + (long long)blockIdx.x * 64 + 8; o[0] = clock64() - tstart; o[1] = w_full; o[2] = w_te; o[3] = w_mma; o[4] = w_cm; o[5] = w_cm2; }
     }
   } else if (p.tma_epi) {
-    // ===================== TMA-staged epilogue (8 warps; plain stride-1 convs) =====================
-    // Warp (sub = warp%4, half = (warp-2)/4) owns accumulator rows [32 sub, 32 sub + 32) = a (32/bw) x bw
-    // sub-patch and the 32-column chunks c = half, half+2, ...  Per chunk: the fp32 residual tile arrives
-    // by TMA (prefetched one chunk ahead, across tiles) in a SWIZZLE_128B staging tile; the thread owning
-    // a row reads its 128 B, adds accumulator + bias (smem copy), writes the fp32 result back IN PLACE and
-    // the activated bf16 operand into a SWIZZLE_64B tile; one lane issues the TMA stores (full lines,
-    // asynchronous, rows/columns outside the tensor are clipped by the tensor map).
+    // ===================== TMA-staged epilogue (plain stride-1 convs) =====================
+    // Warp (sub = warp%4, half = (warp-2)/4) owns accumulator rows [32 sub, 32 sub + 32) = a (32/bw) x bw sub-patch and
+    // the 32-column chunks c = half, half + cs, ... (cs = epi_warps / 4).  It walks its chunk stream n = 0, 1, ... across
+    // tiles.  Per chunk: the fp32 residual tile arrives by TMA in a SWIZZLE_128B staging tile of a ring of R slots,
+    // prefetched R - 1 chunks ahead (R = 4 with 4 warps: a DRAM round trip is longer than one chunk's work -- the fused
+    // pair kernel went from 4.4 to 6.4 TB/s with exactly this change; R = 2 is round 1's scheme); the thread owning a row
+    // reads its 128 B, adds accumulator + bias (smem copy), writes the fp32 result back IN PLACE and the activated operand
+    // into its own tile; one lane issues the TMA stores (full lines, asynchronous, clipped by the tensor map).  Slot
+    // (n + R - 1) % R = (n - 1) % R is free again once the store group of chunk n - 1 has been read out.
     const int ew = warp - 2, sub = warp & 3, half = ew >> 2;
-    uint8_t* const stg = staging + ew * p.epi_warp_bytes;      // [RO0 RO1 (4 KB each, optional)] [AT0 AT1 (2 KB each)]
+    const int cs = (int)(p.epi_warps >> 2);
+    const uint32_t rmask = p.ro_slots - 1;
+    uint8_t* const stg = staging + ew * p.epi_warp_bytes;      // [RO ring (4 KB each, optional)] [AT (1 or 2 tiles)]
     uint8_t* const at_base = stg + p.epi_at_off;
-    uint64_t* const rfull = res_full + ew * 2;
+    uint64_t* const rfull = res_full + ew * p.ro_slots;
     const bool has_res = p.residual != nullptr;
     const int r0 = sub * 32;
     const int dh0 = r0 >> p.tw_log2, dw0 = r0 & ((1 << p.tw_log2) - 1);
     const int nch = p.Ntile >> 5;
-    uint32_t k = 0, rph = 0, acc = 0, acc_ph = 0;               // rph bit b = phase of rfull[b]
+    uint32_t n = 0, rph = 0, acc = 0, acc_ph = 0;               // n: chunk counter of this warp; rph bit b = phase of rfull[b]
     TileIter eit; eit.init(p, blockIdx.x);
-    if (has_res && lane == 0 && blockIdx.x < p.total_tiles && half < nch) {
-      const TileCoord t = eit.coord(p);
-      mbar_expect_tx(&rfull[0], 4096);
-      tma_load_4d(&tmR, &rfull[0], stg, p.r_col + t.n0 + half * 32, t.w0 + dw0, t.h0 + dh0, t.b);
+    TileIter pit; pit.init(p, blockIdx.x);                      // prefetch stream: tile and chunk of the next residual to request
+    int pc = half;
+    uint32_t pn = 0;
+    const uint32_t n_my_e = blockIdx.x < p.total_tiles ? (p.total_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    const uint32_t n_chunks = half < nch ? n_my_e * (uint32_t)((nch - half + cs - 1) / cs) : 0u;
+#pragma unroll 1
+    for (; pn + 1 < p.ro_slots && pn < n_chunks; ++pn) {        // bookkeeping is warp-uniform, lane 0 issues
+      if (has_res && lane == 0) {
+        const TileCoord t = pit.coord(p);
+        mbar_expect_tx(&rfull[pn & rmask], 4096);
+        tma_load_4d(&tmR, &rfull[pn & rmask], stg + (pn & rmask) * 4096, p.r_col + t.n0 + pc * 32, t.w0 + dw0, t.h0 + dh0, t.b);
+      }
+      pc += cs;
+      if (pc >= nch) { pc = half; pit.next(p); }
     }
     const uint32_t sw128 = (uint32_t)(lane & 7) << 4, sw64 = (uint32_t)((lane >> 1) & 3) << 4;
     const bool dbg = p.dbg != nullptr;
@@ -385,17 +401,18 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     for (uint32_t tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
       const long long td0 = dbg ? clock64() : 0;
       const TileCoord t = eit.coord(p);
-      eit.next(p);                                      // eit now points at this CTA's next tile
-      uint32_t bcol = (uint32_t)t.n0 + half * 32;       // bias_s is pre-tiled over the N columns
+      eit.next(p);
       if (dbg) w_dec += clock64() - td0;
       mbar_wait_t(&tmem_full[acc], acc_ph, w_tf, dbg);
       tc_fence_after();
       const uint32_t t_row = tmem_base + ((uint32_t)(sub * 32) << 16) + acc * p.Ntile;
 #pragma unroll 1
-      for (int c = half; c < nch; c += 2) {
+      for (int c = half; c < nch; c += cs, ++n) {
         const int col = t.n0 + c * 32;
-        uint8_t* const ro = stg + k * 4096 + lane * 128;
-        if (has_res) { mbar_wait_t(&rfull[k], (rph >> k) & 1, w_rf, dbg); rph ^= 1u << k; }
+        const uint32_t slot = n & rmask, k = n & 1u;
+        uint32_t bcol = (uint32_t)col;                    // bias_s is pre-tiled over the N columns
+        uint8_t* const ro = stg + slot * 4096 + lane * 128;
+        if (has_res) { mbar_wait_t(&rfull[slot], (rph >> slot) & 1, w_rf, dbg); rph ^= 1u << slot; }
         uint32_t v[32];
         { const long long t0 = dbg ? clock64() : 0; tc_ld32(t_row + c * 32, v); if (dbg) w_ld += clock64() - t0; }
         const long long tq0 = dbg ? clock64() : 0;
@@ -409,7 +426,6 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             f[4 * j + 2] = __uint_as_float(v[4 * j + 2]) + b4.z; f[4 * j + 3] = __uint_as_float(v[4 * j + 3]) + b4.w;
           }
         }
-        bcol += 64;
         if (has_res) {
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
@@ -441,8 +457,8 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             __syncwarp();
           }
           if (p.act_scale) {                          // fused eval-mode BatchNorm of the consumer
-            const float4* sp = reinterpret_cast<const float4*>(asc_s + bcol - 64);
-            const float4* tp = reinterpret_cast<const float4*>(ash_s + bcol - 64);
+            const float4* sp = reinterpret_cast<const float4*>(asc_s + bcol);
+            const float4* tp = reinterpret_cast<const float4*>(ash_s + bcol);
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
               const float4 s4 = sp[j], t4 = tp[j];
@@ -479,28 +495,24 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         const long long tq2 = dbg ? clock64() : 0;
         if (dbg) { w_math += tq1 - tq0; w_fence += tq2 - tq1; }
         if (lane == 0) {
-          if (p.out_raw) tma_store_4d(&tmO, stg + k * 4096, p.o_col + col, t.w0 + dw0, t.h0 + dh0, t.b);
+          if (p.out_raw) tma_store_4d(&tmO, stg + slot * 4096, p.o_col + col, t.w0 + dw0, t.h0 + dh0, t.b);
           if (p.out_act) tma_store_4d(&tmT, at_base + (p.at_double ? k * p.at_bytes : 0u), p.oa_col + col, t.w0 + dw0, t.h0 + dh0, t.b);
           asm volatile("cp.async.bulk.commit_group;" ::: "memory");
           { const long long t0 = dbg ? clock64() : 0;
-            asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");   // buffers k^1 are free again
+            asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");   // the stores of chunk n-1 have left their buffers
             if (dbg) w_wg += clock64() - t0; }
-          if (has_res) {          // residual of this warp's next chunk (this tile or the next one) -> buffer k^1
-            TileCoord tn = t; int cn = c + 2; bool more = true;
-            if (cn >= nch) {
-              cn = half;
-              more = eit.valid(p);                      // eit already points at this CTA's next tile
-              if (more) tn = eit.coord(p);
-            }
-            if (more) {
-              mbar_expect_tx(&rfull[k ^ 1], 4096);
-              tma_load_4d(&tmR, &rfull[k ^ 1], stg + (k ^ 1) * 4096, p.r_col + tn.n0 + cn * 32, tn.w0 + dw0, tn.h0 + dh0, tn.b);
-            }
+          if (has_res && pn < n_chunks) {     // residual of chunk n + R - 1 -> the slot chunk n - 1 used
+            const TileCoord tp = pit.coord(p);
+            mbar_expect_tx(&rfull[pn & rmask], 4096);
+            tma_load_4d(&tmR, &rfull[pn & rmask], stg + (pn & rmask) * 4096, p.r_col + tp.n0 + pc * 32, tp.w0 + dw0, tp.h0 + dh0, tp.b);
           }
+        }
+        if (pn < n_chunks) {                  // warp-uniform bookkeeping of the prefetch stream
+          ++pn; pc += cs;
+          if (pc >= nch) { pc = half; pit.next(p); }
         }
         __syncwarp();
         if (dbg) w_issue += clock64() - tq2;
-        k ^= 1;
       }
       tc_fence_before();
       mbar_arrive(&tmem_empty[acc]);
@@ -513,9 +525,10 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       if (ew == 0) { long long* q = p.dbg + (long long)blockIdx.x * 64 + 56; q[0] = w_math; q[1] = w_fence; q[2] = w_issue; q[3] = w_dec; }
     }
   } else {
-    // ===================== epilogue (8 warps over 128 TMEM lanes) =====================
+    // ===================== direct epilogue (4 or 8 warps over 128 TMEM lanes) =====================
     const int sub = warp & 3;                         // TMEM sub-partition this warp may access
-    const int half = (warp - 2) >> 2;                 // 0/1: which column chunks (even/odd) this warp takes
+    const int half = (warp - 2) >> 2;                 // 8 warps: 0/1 = even / odd column chunks; 4 warps: 0, every chunk
+    const int cstep = 32 * (int)(p.epi_warps >> 2);
     const int row = sub * 32 + lane;                  // accumulator row = position inside the patch
     uint32_t acc = 0, acc_ph = 0;
     TileIter dit; dit.init(p, blockIdx.x);
@@ -541,13 +554,13 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       tc_fence_after();
       const uint32_t t_row = tmem_base + ((uint32_t)(sub * 32) << 16) + acc * p.Ntile;
 #pragma unroll 1
-      for (; c0 < p.Ntile; c0 += 64) {
+      for (; c0 < p.Ntile; c0 += cstep) {
         uint32_t v[32];
         tc_ld32(t_row + c0, v);
         float4 rnext[8];
-        const bool more = has_res && (c0 + 64 < p.Ntile);
+        const bool more = has_res && (c0 + cstep < p.Ntile);
         if (more) {                                   // next chunk's residual: in flight during this chunk
-          const float4* rp = reinterpret_cast<const float4*>(p.residual + off_r + c0 + 64);
+          const float4* rp = reinterpret_cast<const float4*>(p.residual + off_r + c0 + cstep);
 #pragma unroll
           for (int j = 0; j < 8; ++j) rnext[j] = __ldcs(rp + j);
         }
@@ -719,9 +732,17 @@ int conv_gemm_tc(int precision, const vfx_conv_desc& d, cudaStream_t st) {
   static const bool allow_tma_epi = getenv("VFX_NO_TMA_EPI") == nullptr;
   p.tma_epi = (allow_tma_epi && d.sh == 1 && d.sw == 1 && d.rh == 0 && d.rw == 0 && d.OH == d.Hq && d.OW == d.Wq) ? 1u : 0u;
   if (p.tma_epi && d.N > BIAS_SMEM_FLOATS) p.tma_epi = 0;
-  p.epi_arrivals = 32u * NUM_EPI_WARPS;
+  // Epilogue warps: 4 with a residual ring of 4 slots prefetched 3 chunks ahead, or 8 with round 1's two-slot ring (one chunk
+  // ahead, even / odd chunks in parallel).  Measured on one B200 box, B = 32 (A/B of the whole step, VFX_EPI_WARPS=4|8):
+  //   bf16 residual convolutions gain from the deep ring -- ResStack conv2 C = 128: 11.8 -> 10.2 ms per step, C = 256: 8.4 -> 8.1,
+  //   UNet 3x3: 15.6 -> 14.4;  operand-only convolutions lose (their chunks then run serially: C = 128 conv1 5.0 -> 5.8 ms) and
+  //   so does tf32 (already at 6.1 TB/s in conv2; its single operand staging tile serialises the chunks of a warp).
+  static const int epi_env = getenv("VFX_EPI_WARPS") ? atoi(getenv("VFX_EPI_WARPS")) : 0;
+  p.epi_warps = epi_env == 8 ? 8u : epi_env == 4 ? 4u : ((!tf32 && d.residual) ? 4u : 8u);
+  p.ro_slots = p.epi_warps == 8 ? 2u : 4u;
+  p.epi_arrivals = 32u * p.epi_warps;
   const bool needs_ro = d.out_raw || d.residual;
-  p.epi_at_off = needs_ro ? 8192u : 0u;
+  p.epi_at_off = needs_ro ? p.ro_slots * 4096u : 0u;
   // activated-operand staging: bf16 2 x 2 KB (double-buffered); tf32 one 4 KB tile (8 warps x 16 KB next to the
   // raw/residual tiles would leave no room for the operand stages)
   p.at_bytes = tf32 ? 4096u : 2048u;
@@ -729,8 +750,8 @@ int conv_gemm_tc(int precision, const vfx_conv_desc& d, cudaStream_t st) {
                                      // had two halo stages and ran latency-bound at 70 % of HBM)
   p.epi_warp_bytes = p.epi_at_off + (d.out_act ? p.at_bytes * (p.at_double ? 2u : 1u) : 0u);
   p.bias_floats = ((uint32_t)d.N + 63u) & ~63u;
-  p.epi_warps = Ntile >= 64 ? (uint32_t)NUM_EPI_WARPS : 4u;       // warps 2..5 (chunk parity 0) are the only ones with work at Ntile = 32
-  const uint32_t epi_smem = p.tma_epi ? p.epi_warps * p.epi_warp_bytes + 3 * p.bias_floats * 4 : 0u;
+  p.stag_warps = (p.epi_warps == 8 && Ntile < 64) ? 4u : p.epi_warps;   // 8 warps at Ntile = 32: only the even-chunk warps have work
+  const uint32_t epi_smem = p.tma_epi ? p.stag_warps * p.epi_warp_bytes + 3 * p.bias_floats * 4 : 0u;
   if (p.w_resident && p.w_bytes + epi_smem + 3 * p.a_stage_bytes > SMEM_BUDGET) { p.w_resident = 0; p.w_bytes = 0; }
   p.bw_log2 = p.tw_log2 < 5 ? p.tw_log2 : 5;
   // halo mode (resident weights): 1-D conv with taps (-d, 0, +d), d <= 64; or a 3x3 conv (taps in kh,kw order)
@@ -867,8 +888,8 @@ int conv_gemm_tc(int precision, const vfx_conv_desc& d, cudaStream_t st) {
   switch (act) {
 #define VFX_TC_LAUNCH(A)                                                                                       \
   case A:                                                                                                      \
-    if (tf32) conv_gemm_tc_kernel<A, true><<<grid, NUM_THREADS, smem_bytes, st>>>(tmA, tmW, tmR, tmO, tmT, p);  \
-    else conv_gemm_tc_kernel<A, false><<<grid, NUM_THREADS, smem_bytes, st>>>(tmA, tmW, tmR, tmO, tmT, p);      \
+    if (tf32) conv_gemm_tc_kernel<A, true><<<grid, 64 + 32 * (int)p.epi_warps, smem_bytes, st>>>(tmA, tmW, tmR, tmO, tmT, p);  \
+    else conv_gemm_tc_kernel<A, false><<<grid, 64 + 32 * (int)p.epi_warps, smem_bytes, st>>>(tmA, tmW, tmR, tmO, tmT, p);      \
     break
     VFX_TC_LAUNCH(VFX_ACT_NONE); VFX_TC_LAUNCH(VFX_ACT_LRELU); VFX_TC_LAUNCH(VFX_ACT_ELU);
     VFX_TC_LAUNCH(VFX_ACT_LRELU_XSINX); VFX_TC_LAUNCH(VFX_ACT_SIGMOID);
