@@ -164,11 +164,16 @@ enum vfx_act { VFX_ACT_NONE = 0, VFX_ACT_LRELU = 1, VFX_ACT_ELU = 2,
 /* impl: 0 = SIMT, 1 = tcgen05 (BF16 or TF32). */
 int vfx_conv_gemm(int precision, int impl, const vfx_conv_desc* d, void* stream);
 
-/* Fused ResStack pair (bf16 operands, tcgen05; C = 64 only, VFX_ERR_UNSUPPORTED otherwise):
- *   x' = x + conv2_{k3,d=1}( lrelu_0.01( conv1_{k3,dilation}( a ) + b1 ) ) + b2,   a = lrelu_0.01(x) as bf16
- * ResStack.forward voicefixer/vocoder/model/modules.py:592-595 (layers :550-576).  The intermediate never leaves the
- * SM.  x [B][L][C] fp32 is read as the residual and, if write_raw, overwritten with x'; out_act (optional, bf16
- * [B][L][C], must not alias a) receives act(x') for the next consumer.  w1 / w2: [3][C][C] bf16, tap-major. */
+/* Fused ResStack pair on tcgen05:
+ *   x' = x + conv2_{k3,d=1}( lrelu_0.01( conv1_{k3,dilation}( a ) + b1 ) ) + b2
+ * ResStack.forward voicefixer/vocoder/model/modules.py:592-595 (layers :550-576).  The intermediate never leaves the chip.
+ * Two implementations (impl: 0 = pick, 1 = one CTA per tile, 2 = two-CTA cluster pipeline: conv1 on one SM, conv2 on its
+ * neighbour, the intermediate crossing through distributed shared memory):
+ *   VFX_PREC_BF16, C = 64 (impl 1 or 2), C = 128 (impl 2): a = lrelu_0.01(x) as bf16 [B][L][C]; x fp32 is read as the residual
+ *     and, if write_raw, overwritten with x' (or written to x_out); out_act (optional, bf16, must not alias a) receives act(x').
+ *   VFX_PREC_TF32, C = 64 (impl 2), stream_enc = 1: a == x == the encoded stream S (vfx_conv_desc.raw_enc), fp32 [B][L][C];
+ *     the result goes to x_out (required, aliasing neither input) as S' (stream_enc_out = 1) or as plain x' (0).
+ * w1 / w2: [3][C][C] in the operand format, tap-major.  Other shapes return VFX_ERR_UNSUPPORTED. */
 typedef struct vfx_pair_desc {
   const void* a;
   float* x;
@@ -177,6 +182,10 @@ typedef struct vfx_pair_desc {
   int B, L, C;
   int write_raw;
   void* out_act; int act; float act_param;
+  int precision;            /* vfx_precision: VFX_PREC_BF16 (0 is read as BF16 for compatibility) or VFX_PREC_TF32 */
+  int impl;
+  float* x_out;             /* NULL = in place over x (bf16 only) */
+  int stream_enc, stream_enc_out;
 } vfx_pair_desc;
 int vfx_resstack_pair(const vfx_pair_desc* d, void* stream);
 

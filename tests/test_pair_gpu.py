@@ -87,3 +87,75 @@ def test_pair_rejects_other_widths():
     b = _rnd(128, seed=23)
     with pytest.raises(VfxError, match="unsupported"):
         _pair(x, a, w, b, w, b, 1)
+
+
+# ---------------------------------------------------------------------------- two-CTA cluster pipeline (impl = 2)
+def _desc(lib_mod, **kw):
+    d = lib_mod.PairDesc()
+    for k, v in kw.items():
+        setattr(d, k, v)
+    return d
+
+
+@pytest.mark.parametrize("C,L,dil,B", [(128, 1000, 1, 2), (128, 5000, 27, 1), (128, 700, 243, 2), (128, 20000, 9, 3),
+                                       (128, 9000, 2187, 1), (128, 125, 1, 1)])
+def test_pair2_bf16_matches_two_convolutions(C, L, dil, B):
+    """conv1 on one SM, conv2 on its cluster neighbour, h through distributed shared memory: same arithmetic as impl 1."""
+    from voicefixer_b200 import _lib
+    lib = _lib.load()
+    torch.backends.cudnn.allow_tf32 = False
+    x = _rnd(B, L, C, seed=1)
+    a = F.leaky_relu(x, 0.01).bfloat16()
+    w1, w2 = _rnd(C, C, 3, seed=2, scale=0.06).bfloat16(), _rnd(C, C, 3, seed=3, scale=0.06).bfloat16()
+    b1, b2 = _rnd(C, seed=4, scale=0.1), _rnd(C, seed=5, scale=0.1)
+    ref = _ref(x, a, w1, b1, w2, b2, dil)
+    xin = x.clone()
+    w1p, w2p = w1.permute(2, 0, 1).contiguous(), w2.permute(2, 0, 1).contiguous()
+    act = torch.zeros(B, L, C, device=DEV, dtype=torch.bfloat16)
+    d = _desc(_lib, a=a.data_ptr(), x=xin.data_ptr(), w1=w1p.data_ptr(), b1=b1.data_ptr(), dilation=dil, w2=w2p.data_ptr(),
+              b2=b2.data_ptr(), B=B, L=L, C=C, write_raw=1, out_act=act.data_ptr(), act=_lib.ACT["lrelu"], act_param=0.01,
+              precision=_lib.PREC["bf16"], impl=2)
+    _lib.check(lib.vfx_resstack_pair(ctypes.byref(d), ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)), "pair2")
+    torch.cuda.synchronize()
+    assert rel_rms((xin - x).cpu(), (ref - x).cpu()) < 1e-4
+    assert rel_rms(act.float().cpu(), F.leaky_relu(ref, 0.01).cpu()) < 4e-3
+
+
+def _enc(x, slope=0.01):
+    y = F.leaky_relu(x, slope).contiguous()
+    return (y.view(torch.int32) + 0x1000).view(torch.float32)
+
+
+def _dec(s, slope=0.01):
+    y = (s.contiguous().view(torch.int32) - 0x1000).view(torch.float32)
+    return torch.where(y > 0, y, y / slope)
+
+
+@pytest.mark.parametrize("L,dil,B,enc_out", [(1000, 1, 2, 1), (5000, 81, 1, 1), (3000, 9, 2, 0), (20000, 729, 2, 1)])
+def test_pair2_tf32_encoded_stream(L, dil, B, enc_out):
+    """tf32, C = 64: the encoded stream S is operand and residual carrier; the result goes to the other buffer as S' (or as
+    plain x' for the last pair of a stack).  Reference: tf32-rounded operands and intermediate, fp32 accumulation."""
+    from voicefixer_b200 import _lib
+    from voicefixer_b200.weights import round_tf32
+    lib = _lib.load()
+    torch.backends.cudnn.allow_tf32 = False
+    C = 64
+    rt = lambda t: round_tf32(t.cpu()).to(DEV)
+    x = _rnd(B, L, C, seed=41)
+    S = _enc(x)
+    w1, w2 = rt(_rnd(C, C, 3, seed=42, scale=0.08)), rt(_rnd(C, C, 3, seed=43, scale=0.08))
+    b1, b2 = _rnd(C, seed=44, scale=0.1), _rnd(C, seed=45, scale=0.1)
+    a_ref = rt(F.leaky_relu(x, 0.01))
+    h = rt(F.leaky_relu(F.conv1d(a_ref.permute(0, 2, 1), w1, b1, dilation=dil, padding=dil), 0.01))
+    ref = _dec(S) + F.conv1d(h, w2, b2, padding=1).permute(0, 2, 1)
+    out = torch.zeros_like(S)
+    w1p, w2p = w1.permute(2, 0, 1).contiguous(), w2.permute(2, 0, 1).contiguous()
+    d = _desc(_lib, a=S.data_ptr(), x=S.data_ptr(), w1=w1p.data_ptr(), b1=b1.data_ptr(), dilation=dil, w2=w2p.data_ptr(),
+              b2=b2.data_ptr(), B=B, L=L, C=C, write_raw=1, precision=_lib.PREC["tf32"], impl=2, x_out=out.data_ptr(),
+              stream_enc=1, stream_enc_out=enc_out)
+    keep = S.clone()
+    _lib.check(lib.vfx_resstack_pair(ctypes.byref(d), ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)), "pair2")
+    torch.cuda.synchronize()
+    assert torch.equal(S, keep)                                            # the input stream is untouched
+    got = _dec(out) if enc_out else out
+    assert rel_rms((got - x).cpu(), (ref - x).cpu()) < 1e-4

@@ -36,7 +36,8 @@ class ConvDesc(ctypes.Structure):
 class PairDesc(ctypes.Structure):
     """struct vfx_pair_desc (include/vfx_b200.h)."""
     _fields_ = [("a", _vp), ("x", _vp), ("w1", _vp), ("b1", _vp), ("dilation", _i), ("w2", _vp), ("b2", _vp),
-                ("B", _i), ("L", _i), ("C", _i), ("write_raw", _i), ("out_act", _vp), ("act", _i), ("act_param", _f)]
+                ("B", _i), ("L", _i), ("C", _i), ("write_raw", _i), ("out_act", _vp), ("act", _i), ("act_param", _f),
+                ("precision", _i), ("impl", _i), ("x_out", _vp), ("stream_enc", _i), ("stream_enc_out", _i)]
 
 
 # name -> (restype, argtypes); must list every symbol include/vfx_b200.h declares

@@ -4,6 +4,7 @@
 // (Hann window, FFT twiddles) are allocated here at create time.
 #include <math.h>
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 #include <mutex>
 #include <unordered_map>
@@ -43,6 +44,7 @@ struct vfx_engine {
   int parts = 0;    // VFX_PART_* bits of the weight sets found complete by vfx_engine_finalize
   int tf32_stream = 1;  // TF32: vocoder residual streams are kept as ONE encoded fp32 tensor (operand + residual carrier)
   int fuse_pair = 1;  // BF16: ResStack pairs of width 64 run as ONE fused kernel (resstack_pair_tc.cu)
+  int fuse_pair2 = 0; // two-CTA cluster pipeline (resstack_pair2_tc.cu): BF16 width 128, TF32 width 64 (encoded stream)
   int profile = 0;
   std::vector<vfx::ProfRec> prof;
   std::string prof_report;
@@ -577,15 +579,39 @@ int vocoder_generator(Ctx& c, const void* cond, int B, int Tc, float* wav_out, i
     // ---- ResStack: 8 x (x + conv_k3_d1(lrelu(conv_k3_d3^i(lrelu(x))))), modules.py:550-576,592-595
     // bf16, width 64: each pair is ONE fused kernel (h stays on chip); the activated operand copy ping-pongs between
     // A0 and Hh because a pair reads it with a halo that neighbouring tiles would overwrite in place.
-    const bool fuse_pairs = prec == VFX_PREC_BF16 && c.e->use_tc && c.e->fuse_pair && Co == 64;
+    const bool fuse_pairs = prec == VFX_PREC_BF16 && c.e->use_tc &&
+                            ((c.e->fuse_pair && Co == 64) || (c.e->fuse_pair2 && Co == 128));
+    // tf32, width 64: the encoded stream ping-pongs between X and the (otherwise unused) operand buffer; 8 pairs end in X
+    const bool fuse_tf32 = enc && c.e->fuse_pair2 && Co == 64 && j == 3;
     void* a_cur = A0; void* a_nxt = Hh;
+    float* s_cur = X; float* s_nxt = (float*)A0;
     int dil = 1;
     for (int i = 0; i < 8; ++i, dil *= 3) {
       snprintf(name, sizeof(name), "voc.rs%d.l%d", j, i);
       const std::string p(name);
+      if (fuse_tf32) {
+        vfx_pair_desc pd;
+        memset(&pd, 0, sizeof(pd));
+        pd.a = s_cur; pd.x = s_cur; pd.x_out = s_nxt; pd.dilation = dil; pd.B = B; pd.L = (int)Lout; pd.C = Co;
+        pd.w1 = getw(c, p + ".c1.w", (size_t)3 * Co * Co, prec); pd.b1 = getf(c, p + ".c1.b", Co);
+        pd.w2 = getw(c, p + ".c2.w", (size_t)3 * Co * Co, prec); pd.b2 = getf(c, p + ".c2.b", Co);
+        pd.write_raw = 1; pd.precision = VFX_PREC_TF32; pd.impl = 2;
+        pd.stream_enc = 1; pd.stream_enc_out = i < 7 ? 1 : 0;     // the last pair hands plain x' to the final convolution
+        if (!c.dry && c.rc == VFX_OK) {
+          char pt[48], ptd[64];
+          snprintf(pt, sizeof(pt), "voc.rs%d.pair", j);
+          snprintf(ptd, sizeof(ptd), "%s.d%d", pt, dil);
+          const double els = (double)B * Lout * Co;
+          ProfScope ps(c, c.e->profile > 1 ? ptd : pt, 2.0 * 2.0 * 3.0 * Co * els, 8.0 * els);
+          VFX_TRY(resstack_pair2_tc(pd, c.st));
+        }
+        float* t = s_cur; s_cur = s_nxt; s_nxt = t;
+        continue;
+      }
       if (fuse_pairs) {
         vfx_pair_desc pd;
         memset(&pd, 0, sizeof(pd));
+        pd.precision = VFX_PREC_BF16; pd.impl = Co == 64 ? 1 : 2;
         pd.a = a_cur; pd.x = X; pd.dilation = dil; pd.B = B; pd.L = (int)Lout; pd.C = Co;
         pd.w1 = getw(c, p + ".c1.w", (size_t)3 * Co * Co, prec); pd.b1 = getf(c, p + ".c1.b", Co);
         pd.w2 = getw(c, p + ".c2.w", (size_t)3 * Co * Co, prec); pd.b2 = getf(c, p + ".c2.b", Co);
@@ -600,7 +626,7 @@ int vocoder_generator(Ctx& c, const void* cond, int B, int Tc, float* wav_out, i
           const double els = (double)B * Lout * Co;
           // algorithmic bytes of a pair: x in + x' out, fp32
           ProfScope ps(c, c.e->profile > 1 ? ptd : pt, 2.0 * 2.0 * 3.0 * Co * els, 8.0 * els);
-          VFX_TRY(resstack_pair_tc(pd, c.st));
+          VFX_TRY(pd.impl == 1 ? resstack_pair_tc(pd, c.st) : resstack_pair2_tc(pd, c.st));
         }
         void* t = a_cur; a_cur = a_nxt; a_nxt = t;
         continue;
@@ -718,6 +744,7 @@ int vfx_engine_create(vfx_engine** out, int device, int precision) {
   }
   vfx_engine* e = new vfx_engine();
   e->device = device; e->precision = precision;
+  if (getenv("VFX_FUSE_PAIR2")) e->fuse_pair2 = atoi(getenv("VFX_FUSE_PAIR2"));      // A/B knob for bench runs
   std::vector<float> win(2048);
   std::vector<float2> tw(1024);
   for (int n = 0; n < 2048; ++n) win[n] = (float)(0.5 - 0.5 * cos(2.0 * M_PI * n / 2048.0));
@@ -778,6 +805,7 @@ int vfx_engine_set_option(vfx_engine* e, const char* key, int value) {
   if (!strcmp(key, "use_tc")) { e->use_tc = value; return VFX_OK; }
   if (!strcmp(key, "profile")) { e->profile = value; return VFX_OK; }
   if (!strcmp(key, "fuse_pair")) { e->fuse_pair = value; return VFX_OK; }
+  if (!strcmp(key, "fuse_pair2")) { e->fuse_pair2 = value; return VFX_OK; }
   if (!strcmp(key, "tf32_stream")) { e->tf32_stream = value; return VFX_OK; }
   set_error("set_option: unknown key '%s'", key);
   return VFX_ERR_INVALID;
@@ -975,8 +1003,12 @@ int vfx_conv_gemm(int precision, int impl, const vfx_conv_desc* d, void* stream)
 
 int vfx_resstack_pair(const vfx_pair_desc* d, void* stream) {
   VFX_REQUIRE(d, "resstack_pair: null descriptor");
-  int r = resstack_pair_tc(*d, (cudaStream_t)stream);
-  if (r == VFX_ERR_UNSUPPORTED) set_error("resstack_pair: unsupported shape (C must be 64, 16-byte aligned tensors)");
+  const bool tf32 = d->precision == VFX_PREC_TF32;
+  const bool one_cta = d->impl == 1 || (d->impl == 0 && !tf32 && d->C == 64 && !d->x_out);
+  int r = one_cta ? ((tf32 || d->x_out) ? VFX_ERR_UNSUPPORTED : resstack_pair_tc(*d, (cudaStream_t)stream))
+                  : resstack_pair2_tc(*d, (cudaStream_t)stream);
+  if (r == VFX_ERR_UNSUPPORTED)
+    set_error("resstack_pair: unsupported shape (bf16: C = 64 or 128; tf32: C = 64 with stream_enc; 16-byte aligned tensors)");
   return r;
 }
 
