@@ -15,7 +15,8 @@ of synthetic degraded utterances.  N = 1: BASELINE configs[2], 32 x 10 s, mode 0
           step's inputs, the launch sequence, D2H of the waveforms, every step.  N > 1: per rank H2D of its shard ->
           launch sequence -> NCCL gather -> rank 0 copies the WHOLE gathered result to its host.
   dtype   the headline runs at the reference CUDA path's arithmetic class, tf32 (cuDNN TF32 convolutions, SURVEY D10);
-          the bf16 mode is measured in the same run and reported under `modes`.
+          the fp16 mode (tf32's 10-bit mantissa in 2-byte operands: tf32's parity at bf16's speed, within fp16's exponent
+          range) and the bf16 mode are measured in the same run and reported under `modes`, each with its own parity.
 
 The N = 1 line also carries: `roofline` (ResStack pair unit of SURVEY 8d), `cpu_baseline` (oracle port on the host cores,
 bounded sample), `parity` (waveform error of each precision against that oracle output; out of tolerance FAILS the run),
@@ -182,8 +183,8 @@ def run_reference(args):
 
 
 
-TOL = {"tf32": (2e-3, 1e-3), "bf16": (3e-2, 5e-3), "fp32": (2e-4, 1e-4)}      # (rel-RMS, mean-abs) vs the oracle, tests/test_parity_gpu.py
-DTYPE = {"bf16": "bf16", "tf32": "tf32", "fp32": "f32"}
+TOL = {"tf32": (2e-3, 1e-3), "fp16": (2e-3, 1e-3), "bf16": (3e-2, 5e-3), "fp32": (2e-4, 1e-4)}      # (rel-RMS, mean-abs) vs the oracle, tests/test_parity_gpu.py
+DTYPE = {"bf16": "bf16", "tf32": "tf32", "fp32": "f32", "fp16": "f16"}
 
 
 def wl_longform(vf, steps=2, modes=(0, 1, 2)):
@@ -342,7 +343,7 @@ def roofline_from(rep, B, L_by_stack, precision, peaks, peaks_src, tot_ms):
     tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
     if os.path.exists(tpath):
         tj = json.load(open(tpath))
-        ent = tj.get(f"{precision}:voc.rs{dom['j']}.pair:B{B}")
+        ent = tj.get(f"{'bf16' if precision == 'fp16' else precision}:voc.rs{dom['j']}.pair:B{B}")       # fp16 moves bf16's bytes
         if ent and ent.get("csrc_sha") == csrc_sha(ent.get("files")):
             traffic, tnote = ent["dram_bytes_per_pair"], ent.get("source", "profiles/")
         elif ent:
@@ -642,18 +643,18 @@ def main():
         except Exception as e:
             workloads["batch64_1gpu"] = {"error": f"{type(e).__name__}: {e}"}
         gc.collect(); torch.cuda.empty_cache()
-        other = "bf16" if prec != "bf16" else "tf32"
-        try:
-            r2 = measure_batch(a2, other, rank, world, local, B, full=False)
-            rep2 = r2["rep"]
-            modes[other] = {"dtype": DTYPE[other], "value": r2["value"], "ms_per_step": r2["ms_per_step"], "e2e": r2["e2e"]["value"],
-                            "roofline": roofline_from(rep2, B, L_by_stack, other, peaks, peaks_src, sum(r["ms"] for r in rep2.values())),
-                            "breakdown_ms": r2["breakdown_ms"],
-                            "parity": parity_of(r2["eng"], run.wav, run.out, other) if run is not None else None}
-            del r2
-        except Exception as e:
-            modes[other] = {"error": f"{type(e).__name__}: {e}"}
-        gc.collect(); torch.cuda.empty_cache()
+        for other in [m for m in ("fp16", "bf16", "tf32") if m != prec][:2]:
+            try:
+                r2 = measure_batch(a2, other, rank, world, local, B, full=False)
+                rep2 = r2["rep"]
+                modes[other] = {"dtype": DTYPE[other], "value": r2["value"], "ms_per_step": r2["ms_per_step"], "e2e": r2["e2e"]["value"],
+                                "roofline": roofline_from(rep2, B, L_by_stack, other, peaks, peaks_src, sum(r["ms"] for r in rep2.values())),
+                                "breakdown_ms": r2["breakdown_ms"],
+                                "parity": parity_of(r2["eng"], run.wav, run.out, other) if run is not None else None}
+                del r2
+            except Exception as e:
+                modes[other] = {"error": f"{type(e).__name__}: {e}"}
+            gc.collect(); torch.cuda.empty_cache()
         try:
             workloads["cli_folder"] = wl_cli(prec)
         except Exception as e:

@@ -36,8 +36,11 @@ enum vfx_status {
  *   TF32: tcgen05 tensor-core MMA (kind::tf32), fp32 storage with operands and weights rounded to tf32
  *         (round-to-nearest) by their producers, fp32 accumulation -- the arithmetic of the reference's own
  *         CUDA path (torch.backends.cudnn.allow_tf32 defaults to True; the reference's test/test.py:27-35
- *         compares that path with its CPU path).  Weights are registered in the FP32 layout. */
-enum vfx_precision { VFX_PREC_FP32 = 0, VFX_PREC_BF16 = 1, VFX_PREC_TF32 = 2 };
+ *         compares that path with its CPU path).  Weights are registered in the FP32 layout.
+ *   FP16: tcgen05 kind::f16 on fp16 operands and weights, fp32 accumulation: the SAME 10-bit mantissa as tf32 (so the same
+ *         waveform parity) in 2-byte storage, i.e. the BF16 mode's memory traffic, kernels and speed -- at fp16's exponent
+ *         range (|x| < 65504; smaller than 6e-5 loses relative precision).  Everything outside the GEMM operands stays fp32. */
+enum vfx_precision { VFX_PREC_FP32 = 0, VFX_PREC_BF16 = 1, VFX_PREC_TF32 = 2, VFX_PREC_FP16 = 3 };
 
 /* restore() modes, voicefixer/base.py:110-115. mode 1's pre-filter is vfx_hf_cut(). */
 enum vfx_mode { VFX_MODE_EVAL = 0, VFX_MODE_TRAIN_BN = 2 };
@@ -58,7 +61,10 @@ int vfx_engine_destroy(vfx_engine* e);
  * Replaces torch.load + load_state_dict: voicefixer/base.py:15-30, voicefixer/vocoder/base.py:24-32. */
 int vfx_engine_set_tensor(vfx_engine* e, const char* name, const void* dev_ptr, size_t bytes);
 /* Engine options: "use_tc" (BF16 / TF32; 1 = tcgen05 kernel [default], 0 = SIMT cross-check on the same operands),
- * "profile" (0/1, see vfx_profile_report). */
+ * "profile" (0/1/2, see vfx_profile_report; 2 = one tag per shape / dilation),
+ * "fuse_pair" (BF16: width-64 ResStack pairs as one fused kernel, default 1),
+ * "tf32_stream" (TF32: vocoder residual streams as one encoded tensor, vfx_conv_desc.res_enc / raw_enc, default 1),
+ * "fuse_pair2" (two-CTA cluster pipeline for BF16 width 128 / TF32 width 64 pairs: correct but slower, default 0). */
 int vfx_engine_set_option(vfx_engine* e, const char* key, int value);
 /* Number of CUDA kernels this library has launched in this process (bench.py's gpu_launches). */
 unsigned long long vfx_launch_count(void);
@@ -161,7 +167,7 @@ typedef struct vfx_conv_desc {
 enum vfx_act { VFX_ACT_NONE = 0, VFX_ACT_LRELU = 1, VFX_ACT_ELU = 2,
                VFX_ACT_LRELU_XSINX = 3 /* v = lrelu(x, p); v + sin v */, VFX_ACT_SIGMOID = 4 };
 
-/* impl: 0 = SIMT, 1 = tcgen05 (BF16 or TF32). */
+/* impl: 0 = SIMT, 1 = tcgen05 (BF16, TF32 or FP16). */
 int vfx_conv_gemm(int precision, int impl, const vfx_conv_desc* d, void* stream);
 
 /* Fused ResStack pair on tcgen05:

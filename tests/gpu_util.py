@@ -23,7 +23,7 @@ def conv_gemm(a, w, taps, Hq=None, Wq=None, N=None, w_off=None, bias=None, bias_
     d.sh, d.rh, d.sw, d.rw = sh, rh, sw, rw
     d.OH, d.OW = OH or d.Hq, OW or d.Wq
     ld = out_ld or N
-    dt = torch.bfloat16 if precision == "bf16" else torch.float32      # tf32: fp32 storage
+    dt = {"bf16": torch.bfloat16, "fp16": torch.float16}.get(precision, torch.float32)      # tf32: fp32 storage
     if want_raw:
         if out_raw is None:
             out_raw = torch.zeros(B, d.OH, d.OW, ld, device=a.device)

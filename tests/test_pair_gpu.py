@@ -19,19 +19,20 @@ def _rnd(*shape, seed=0, scale=1.0):
     return (torch.randn(*shape, generator=g) * scale).to(DEV)
 
 
-def _pair(x, a, w1, b1, w2, b2, dil, write_raw=True, act="lrelu", act_param=0.01, want_act=True):
-    """x (B,L,C) fp32 [updated in place], a (B,L,C) bf16, w (C,C,3) bf16 torch layout."""
+def _pair(x, a, w1, b1, w2, b2, dil, write_raw=True, act="lrelu", act_param=0.01, want_act=True, prec="bf16"):
+    """x (B,L,C) fp32 [updated in place], a (B,L,C) bf16 / fp16, w (C,C,3) same format, torch layout."""
     from voicefixer_b200 import _lib
     lib = _lib.load()
     B, L, C = x.shape
     d = _lib.PairDesc()
     w1p, w2p = w1.permute(2, 0, 1).contiguous(), w2.permute(2, 0, 1).contiguous()
-    out_act = torch.zeros(B, L, C, device=DEV, dtype=torch.bfloat16) if want_act else None
+    out_act = torch.zeros(B, L, C, device=DEV, dtype=a.dtype) if want_act else None
     d.a, d.x = a.data_ptr(), x.data_ptr()
     d.w1, d.b1, d.dilation, d.w2, d.b2 = w1p.data_ptr(), b1.data_ptr(), dil, w2p.data_ptr(), b2.data_ptr()
     d.B, d.L, d.C, d.write_raw = B, L, C, int(write_raw)
     d.out_act = out_act.data_ptr() if want_act else None
     d.act, d.act_param = _lib.ACT[act], act_param
+    d.precision = _lib.PREC[prec]
     _lib.check(lib.vfx_resstack_pair(ctypes.byref(d), ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)),
                "vfx_resstack_pair")
     torch.cuda.synchronize()
@@ -40,7 +41,7 @@ def _pair(x, a, w1, b1, w2, b2, dil, write_raw=True, act="lrelu", act_param=0.01
 
 def _ref(x, a, w1, b1, w2, b2, dil):
     h = F.leaky_relu(F.conv1d(a.float().permute(0, 2, 1), w1.float(), b1, dilation=dil, padding=dil), 0.01)
-    h = h.bfloat16().float()
+    h = h.to(a.dtype).float()
     return x + F.conv1d(h, w2.float(), b2, padding=1).permute(0, 2, 1)
 
 
@@ -58,6 +59,22 @@ def test_pair_matches_two_convolutions(L, dil, B):
     act = _pair(xin, a, w1, b1, w2, b2, dil)
     assert rel_rms((xin - x).cpu(), (ref - x).cpu()) < 1e-4            # the update itself, not masked by the residual
     assert rel_rms(act.float().cpu(), F.leaky_relu(ref, 0.01).cpu()) < 4e-3
+
+
+@pytest.mark.parametrize("L,dil,B", [(3000, 3, 2), (4000, 243, 1)])
+def test_pair_fp16_operands(L, dil, B):
+    """The same kernel with the other kind::f16 operand format: fp16 a / h / weights (tf32's mantissa in 2 bytes)."""
+    torch.backends.cudnn.allow_tf32 = False
+    C = 64
+    x = _rnd(B, L, C, seed=1)
+    a = F.leaky_relu(x, 0.01).half()
+    w1, w2 = _rnd(C, C, 3, seed=2, scale=0.08).half(), _rnd(C, C, 3, seed=3, scale=0.08).half()
+    b1, b2 = _rnd(C, seed=4, scale=0.1), _rnd(C, seed=5, scale=0.1)
+    ref = _ref(x, a, w1, b1, w2, b2, dil)
+    xin = x.clone()
+    act = _pair(xin, a, w1, b1, w2, b2, dil, prec="fp16")
+    assert rel_rms((xin - x).cpu(), (ref - x).cpu()) < 1e-4
+    assert rel_rms(act.float().cpu(), F.leaky_relu(ref, 0.01).cpu()) < 5e-4
 
 
 def test_pair_output_variants():
@@ -80,11 +97,12 @@ def test_pair_output_variants():
 
 
 def test_pair_rejects_other_widths():
+    """Widths whose weight sets fit neither one SM (64) nor a two-SM pipeline (128) are refused, not mis-computed."""
     from voicefixer_b200._lib import VfxError
-    x = _rnd(1, 200, 128, seed=21)
+    x = _rnd(1, 200, 256, seed=21)
     a = x.bfloat16()
-    w = _rnd(128, 128, 3, seed=22).bfloat16()
-    b = _rnd(128, seed=23)
+    w = _rnd(256, 256, 3, seed=22).bfloat16()
+    b = _rnd(256, seed=23)
     with pytest.raises(VfxError, match="unsupported"):
         _pair(x, a, w, b, w, b, 1)
 

@@ -98,8 +98,9 @@ def test_api_dropin_restore_inmem_and_segmentation(tmp_path, monkeypatch, states
 # error alone, tools/sim_precision.py: tf32 1.7e-3, bf16 1.3e-2 relative RMS):
 #   fp32   rel-RMS 2e-4
 #   tf32   rel-RMS 2e-3, mean-abs 1e-3      (SURVEY 8d's figure; measured 1.65e-3 / 3.5e-4 on the 10 s utterance)
+#   fp16   as tf32: the same 10-bit mantissa (CPU prediction 1.64e-3), 2-byte operands, fp16's exponent range
 #   bf16   rel-RMS 3e-2,   mean-abs 5e-3    (reference's own CPU<->GPU acceptance bar: mean-abs 1e-2, test/test.py:35)
-FULL_TOL = {"fp32": (2e-4, 1e-4), "tf32": (2e-3, 1e-3), "bf16": (3e-2, 5e-3)}
+FULL_TOL = {"fp32": (2e-4, 1e-4), "tf32": (2e-3, 1e-3), "fp16": (2e-3, 1e-3), "bf16": (3e-2, 5e-3)}
 
 
 @pytest.fixture(scope="module")
@@ -111,7 +112,7 @@ def oracle_10s(states):
 
 
 @pytest.mark.timeout(600)
-@pytest.mark.parametrize("prec", ["fp32", "tf32", "bf16"])
+@pytest.mark.parametrize("prec", ["fp32", "tf32", "fp16", "bf16"])
 def test_restore_10s_vs_oracle(states, oracle_10s, prec):
     from voicefixer_b200.engine import Engine
     wav, ref = oracle_10s
@@ -132,7 +133,7 @@ def test_restore_30s_segment_vs_oracle(states):
     wav = synthetic.make_utterances(1, seconds=30.0, seed=4321)[0]
     assert 1 + wav.shape[0] // 441 == 3001
     ref = O.restore_inmem(wav, states[0], states[1], mode=0)
-    for prec in ("tf32", "bf16"):
+    for prec in ("tf32", "fp16", "bf16"):
         out = Engine(states[0], states[1], precision=prec).restore(wav[None]).cpu().numpy()
         tol_rms, tol_mae = FULL_TOL[prec]
         assert rel_rms(out, ref) < tol_rms, prec
@@ -285,6 +286,39 @@ def test_two_cta_pair_pipeline_engine_path(states, oracle_10s, prec):
     y1 = eng.restore(wav[None]).cpu().numpy()
     assert rel_rms(y1, ref) < FULL_TOL[prec][0] and float(np.mean(np.abs(y1 - ref))) < FULL_TOL[prec][1]
     assert rel_rms(y1, y0) < FULL_TOL[prec][0]
+
+
+# ---------------------------------------------------------------------------- fp16 tensor-core path
+# precision "fp16": the bf16 mode's kernels (fused ResStack pair included) with the other kind::f16 operand format.  fp16
+# carries tf32's 10-bit mantissa, so the tolerances are tf32's.
+@pytest.fixture(scope="module")
+def engine_fp16(states):
+    from voicefixer_b200.engine import Engine
+    return Engine(states[0], states[1], precision="fp16")
+
+
+@pytest.mark.parametrize("T", [1, 65, 130])
+def test_fp16_analysis_vs_reference_golden(engine_fp16, T):
+    g = golden(f"analysis_T{T}")
+    assert rel_rms(engine_fp16.analysis(g["mel"][:, 0]).cpu().numpy(), g["out"][:, 0]) < TOL_TF32_STAGE
+
+
+@pytest.mark.parametrize("T", [3, 20])
+def test_fp16_vocoder_vs_reference_golden(engine_fp16, T):
+    g = golden(f"vocoder_T{T}")
+    out = engine_fp16.vocoder(g["mel"][:, 0]).cpu().numpy()
+    assert rel_rms(out, g["out"][:, 0]) < TOL_TF32_WAV
+    assert float(np.mean(np.abs(out - g["out"][:, 0]))) < TOL_TF32_MAE
+
+
+def test_fp16_restore_and_simt_cross_check(engine_fp16):
+    g = golden("restore_mode0")
+    out = engine_fp16.restore(g["wav"][None]).cpu().numpy()
+    assert rel_rms(out, g["out"]) < TOL_TF32_WAV
+    engine_fp16.set_option("use_tc", 0)
+    y_simt = engine_fp16.restore(g["wav"][None]).cpu().numpy()
+    engine_fp16.set_option("use_tc", 1)
+    assert rel_rms(out, y_simt) < TOL_TF32_WAV
 
 
 def test_cuda_graph_replay_matches_direct_launch(engine_bf16):

@@ -24,13 +24,16 @@ def _op(t, prec):
     if prec == "bf16":
         q = t.bfloat16()
         return q, q.float()
+    if prec == "fp16":
+        q = t.half()
+        return q, q.float()
     from voicefixer_b200.weights import round_tf32
     q = round_tf32(t.cpu()).to(DEV)
     return q, q
 
 
-ACT_TOL = {"bf16": 4e-3, "tf32": 5e-4}
-PRECS = ["bf16", "tf32"]
+ACT_TOL = {"bf16": 4e-3, "tf32": 5e-4, "fp16": 5e-4}
+PRECS = ["bf16", "tf32", "fp16"]
 
 
 @pytest.mark.parametrize("C,L,dil,B", [(64, 128, 1, 1), (64, 700, 3, 2), (128, 1000, 27, 1), (256, 333, 243, 2),

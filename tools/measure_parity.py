@@ -8,7 +8,7 @@ from voicefixer_b200 import synthetic
 from voicefixer_b200.engine import Engine
 
 ana, voc = synthetic.make_analysis_state(0), synthetic.make_vocoder_state(1)
-for prec, tc in (("fp32", 1), ("tf32", 0), ("tf32", 1), ("bf16", 0), ("bf16", 1)):
+for prec, tc in (("fp32", 1), ("tf32", 0), ("tf32", 1), ("fp16", 0), ("fp16", 1), ("bf16", 0), ("bf16", 1)):
     eng = Engine(ana, voc, precision=prec)
     if prec != "fp32":
         eng.set_option("use_tc", tc)
@@ -31,6 +31,6 @@ for prec, tc in (("fp32", 1), ("tf32", 0), ("tf32", 1), ("bf16", 0), ("bf16", 1)
 from oracle import vf_oracle as O
 wav = synthetic.make_utterances(1, seconds=10.0, seed=1234)[0]
 ref = O.restore_inmem(wav, ana, voc, mode=0)
-for prec in ("fp32", "tf32", "bf16"):
+for prec in ("fp32", "tf32", "fp16", "bf16"):
     o = Engine(ana, voc, precision=prec).restore(wav[None]).cpu().numpy()
     print(f"10s {prec}: rel_rms={rel_rms(o, ref):.3e} mean_abs={float(np.mean(np.abs(o - ref))):.3e}", flush=True)

@@ -8,6 +8,7 @@ the stated tolerances of the tf32 / bf16 engine modes were derived before the ke
   tf32-rn    cvt.rna.tf32.f32 on both operands (what the engine's tf32 mode does when it writes operands)
   tf32-trunc hardware truncation of raw fp32 operands (what kind::tf32 does to un-rounded inputs)
   bf16       round-to-nearest bf16 operands (the engine's bf16 mode)
+  fp16       round-to-nearest fp16 operands: the same 10-bit mantissa as tf32 in 2 bytes (5-bit exponent)
 
 The reference's own CUDA path runs its convolutions in TF32 (torch.backends.cudnn.allow_tf32 defaults to True,
 SURVEY D10), so the tf32 rows are also the reference GPU path's own deviation from its CPU path.
@@ -38,7 +39,11 @@ def round_bf16(x):
     return x.to(torch.bfloat16).to(torch.float32)
 
 
-MODES = {"tf32-rn": round_tf32_rn, "tf32-trunc": trunc_tf32, "bf16": round_bf16}
+def round_fp16(x):
+    return x.to(torch.float16).to(torch.float32)
+
+
+MODES = {"tf32-rn": round_tf32_rn, "fp16": round_fp16, "tf32-trunc": trunc_tf32, "bf16": round_bf16}
 
 
 class patched:

@@ -9,7 +9,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libvfx_b200.so")
 
 VFX_OK = 0
-PREC = {"fp32": 0, "bf16": 1, "tf32": 2}
+PREC = {"fp32": 0, "bf16": 1, "tf32": 2, "fp16": 3}
 ACT = {"none": 0, "lrelu": 1, "elu": 2, "lrelu_xsinx": 3, "sigmoid": 4}
 
 _c = ctypes

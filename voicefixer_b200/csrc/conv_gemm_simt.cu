@@ -40,6 +40,15 @@ template <> struct Vec8<tf32_t> {
     for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(u[i] & 0xFFFFE000u);
   }
 };
+template <> struct Vec8<__half> {
+  float v[8];
+  __device__ void load(const __half* p) {
+    uint4 r = *reinterpret_cast<const uint4*>(p);
+    const __half2* h = reinterpret_cast<const __half2*>(&r);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { float2 f = __half22float2(h[i]); v[2 * i] = f.x; v[2 * i + 1] = f.y; }
+  }
+};
 template <> struct Vec8<__nv_bfloat16> {
   float v[8];
   __device__ void load(const __nv_bfloat16* p) {
@@ -173,12 +182,14 @@ int conv_gemm_simt(int precision, const vfx_conv_desc& d, cudaStream_t st) {
   VFX_REQUIRE(!d.bias || d.bias_mod > 0, "conv_gemm: bias_mod must be > 0");
   const long long M = (long long)d.B * d.Hq * d.Wq;
   dim3 grid(ceil_div(M, BM), ceil_div(d.N, BN));
-  const int esz = precision == VFX_PREC_BF16 ? 2 : 4;
+  const int esz = (int)prec_esz(precision);
   const int al = 16 / esz;   // elements per 16 bytes
   bool vec_ok = (d.Cin % BK == 0) && (d.a_sB % al == 0) && (d.a_sH % al == 0) && (d.a_sW % al == 0) &&
                 ((uintptr_t)d.a % 16 == 0);
   if (precision == VFX_PREC_BF16)
     conv_gemm_simt_kernel<__nv_bfloat16><<<grid, NT, 0, st>>>(d, vec_ok);
+  else if (precision == VFX_PREC_FP16)
+    conv_gemm_simt_kernel<__half><<<grid, NT, 0, st>>>(d, vec_ok);
   else if (precision == VFX_PREC_TF32)     // fp32 FMA on tf32-rounded operands (products exact): same arithmetic as kind::tf32
     conv_gemm_simt_kernel<tf32_t><<<grid, NT, 0, st>>>(d, vec_ok);
   else

@@ -2,6 +2,7 @@
 // TMA-staged operand tiles -> tcgen05.mma (fp32 accumulators in TMEM) -> fused epilogue.
 // Two operand formats, same kernel (template parameter TF32):
 //   VFX_PREC_BF16  bf16 operands / weights, kind::f16, UMMA K = 16, K chunk = 64 channels (32 if Cin == 32)
+//   VFX_PREC_FP16  fp16 operands / weights: the same kernel as bf16 with the other kind::f16 operand format
 //   VFX_PREC_TF32  fp32 storage rounded to tf32 by the producers, kind::tf32, UMMA K = 8, K chunk = 32 channels
 // (a K chunk is one swizzled 128-byte row -- 64 bytes for the bf16 Cin == 32 case -- so every piece of address
 // arithmetic below is in bytes and shared by both formats; one MMA always advances 32 bytes along K).
@@ -119,7 +120,7 @@ struct TileIter {
   }
 };
 
-template <int ACT, bool TF32>
+template <int ACT, bool TF32, bool FP16>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
                     const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CUtensorMap tmO,
@@ -479,12 +480,8 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             for (int j = 0; j < 4; ++j) {
               uint32_t w[4];
 #pragma unroll
-              for (int q = 0; q < 4; ++q) {
-                const float lo = act_fast<ACT>(f[8 * j + 2 * q], p.act_param);
-                const float hi = act_fast<ACT>(f[8 * j + 2 * q + 1], p.act_param);
-                __nv_bfloat162 h2 = __floats2bfloat162_rn(lo, hi);
-                w[q] = *reinterpret_cast<uint32_t*>(&h2);
-              }
+              for (int q = 0; q < 4; ++q)
+                w[q] = pack16<FP16>(act_fast<ACT>(f[8 * j + 2 * q], p.act_param), act_fast<ACT>(f[8 * j + 2 * q + 1], p.act_param));
               *reinterpret_cast<uint4*>(at + ((uint32_t)(j << 4) ^ sw64)) = make_uint4(w[0], w[1], w[2], w[3]);
             }
           }
@@ -623,12 +620,8 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
               for (int j = 0; j < 4; ++j) {
                 uint32_t w[4];
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                  const float lo = act_fast<ACT>(f[8 * j + 2 * q], p.act_param);
-                  const float hi = act_fast<ACT>(f[8 * j + 2 * q + 1], p.act_param);
-                  __nv_bfloat162 h2 = __floats2bfloat162_rn(lo, hi);
-                  w[q] = *reinterpret_cast<uint32_t*>(&h2);
-                }
+                for (int q = 0; q < 4; ++q)
+                  w[q] = pack16<FP16>(act_fast<ACT>(f[8 * j + 2 * q], p.act_param), act_fast<ACT>(f[8 * j + 2 * q + 1], p.act_param));
                 ap[j] = make_uint4(w[0], w[1], w[2], w[3]);
               }
             }
@@ -660,8 +653,8 @@ int ilog2(int v) { int l = 0; while ((1 << l) < v) ++l; return l; }
 
 int conv_gemm_tc(int precision, const vfx_conv_desc& d, cudaStream_t st) {
   // ---- shapes this kernel covers; everything else returns UNSUPPORTED (caller uses the SIMT kernel)
-  if (precision != VFX_PREC_BF16 && precision != VFX_PREC_TF32) return VFX_ERR_UNSUPPORTED;
-  const bool tf32 = precision == VFX_PREC_TF32;
+  if (precision != VFX_PREC_BF16 && precision != VFX_PREC_TF32 && precision != VFX_PREC_FP16) return VFX_ERR_UNSUPPORTED;
+  const bool tf32 = precision == VFX_PREC_TF32, fp16 = precision == VFX_PREC_FP16;
   const int esz = tf32 ? 4 : 2;
   int KC = 0;
   if (tf32) { if (d.Cin % 32 == 0) KC = 32; }
@@ -709,9 +702,9 @@ int conv_gemm_tc(int precision, const vfx_conv_desc& d, cudaStream_t st) {
   if ((p.res_enc || p.raw_enc) && !(d.enc_slope > 0.f)) { set_error("conv_gemm_tc: enc_slope must be positive"); return VFX_ERR_INVALID; }
   p.enc_slope = d.enc_slope; p.enc_inv_slope = d.enc_slope > 0.f ? 1.0f / d.enc_slope : 0.f;
   p.act_scale = d.out_act ? d.act_scale : nullptr; p.act_shift = d.out_act ? d.act_shift : nullptr;
-  // instruction descriptor: c=F32 [4,6)=1, a/b format [7,10)/[10,13) = 1 (BF16) or 2 (TF32), K-major both,
+  // instruction descriptor: c=F32 [4,6)=1, a/b format [7,10)/[10,13) = 0 (F16), 1 (BF16) or 2 (TF32), K-major both,
   // N>>3 [17,23), M>>4 [24,29)
-  const uint32_t fmt = tf32 ? 2u : 1u;
+  const uint32_t fmt = tf32 ? 2u : fp16 ? 0u : 1u;     // F16F32Format: 0 = F16, 1 = BF16, 2 = TF32
   p.idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(Ntile >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
   const uint32_t row_bytes = KC * esz;
   p.row_bytes = row_bytes;
@@ -812,7 +805,7 @@ int conv_gemm_tc(int precision, const vfx_conv_desc& d, cudaStream_t st) {
   // ---- tensor maps
   CUtensorMap tmA, tmW;
   const CUtensorMapSwizzle swz = row_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
-  const CUtensorMapDataType op_dt = tf32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+  const CUtensorMapDataType op_dt = tf32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : fp16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
   {
     cuuint64_t dims[4] = {(cuuint64_t)d.Cin, (cuuint64_t)d.W, (cuuint64_t)d.H, (cuuint64_t)d.B};
     cuuint64_t strides[3] = {(cuuint64_t)d.a_sW * esz, (cuuint64_t)d.a_sH * esz, (cuuint64_t)d.a_sB * esz};
@@ -852,7 +845,7 @@ int conv_gemm_tc(int precision, const vfx_conv_desc& d, cudaStream_t st) {
     if (r == CUDA_SUCCESS && d.out_raw) r = enc(&tmO, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, d.out_raw, d.o_col + d.N, d.o_sW, d.o_sH, d.o_sB, CU_TENSOR_MAP_SWIZZLE_128B);
     if (r == CUDA_SUCCESS && d.out_act)
       r = tf32 ? enc(&tmT, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, d.out_act, d.oa_col + d.N, d.oa_sW, d.oa_sH, d.oa_sB, CU_TENSOR_MAP_SWIZZLE_128B)
-               : enc(&tmT, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, d.out_act, d.oa_col + d.N, d.oa_sW, d.oa_sH, d.oa_sB, CU_TENSOR_MAP_SWIZZLE_64B);
+               : enc(&tmT, op_dt, 2, d.out_act, d.oa_col + d.N, d.oa_sW, d.oa_sH, d.oa_sB, CU_TENSOR_MAP_SWIZZLE_64B);
     if (r != CUDA_SUCCESS) { set_error("conv_gemm_tc: cuTensorMapEncodeTiled(epilogue) failed with %d", (int)r); return VFX_ERR_CUDA; }
   }
 
@@ -868,9 +861,10 @@ int conv_gemm_tc(int precision, const vfx_conv_desc& d, cudaStream_t st) {
   if (dev < 64 && sms_of[dev]) num_sms = sms_of[dev];
   else {
     VFX_CUDA_CHECK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
-#define VFX_TC_ATTR(A)                                                                                                              \
-  VFX_CUDA_CHECK(cudaFuncSetAttribute(conv_gemm_tc_kernel<A, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); \
-  VFX_CUDA_CHECK(cudaFuncSetAttribute(conv_gemm_tc_kernel<A, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024))
+#define VFX_TC_ATTR(A)                                                                                                                     \
+  VFX_CUDA_CHECK(cudaFuncSetAttribute(conv_gemm_tc_kernel<A, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); \
+  VFX_CUDA_CHECK(cudaFuncSetAttribute(conv_gemm_tc_kernel<A, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));  \
+  VFX_CUDA_CHECK(cudaFuncSetAttribute(conv_gemm_tc_kernel<A, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024))
     VFX_TC_ATTR(VFX_ACT_NONE); VFX_TC_ATTR(VFX_ACT_LRELU); VFX_TC_ATTR(VFX_ACT_ELU); VFX_TC_ATTR(VFX_ACT_LRELU_XSINX);
     VFX_TC_ATTR(VFX_ACT_SIGMOID);
 #undef VFX_TC_ATTR
@@ -888,8 +882,9 @@ int conv_gemm_tc(int precision, const vfx_conv_desc& d, cudaStream_t st) {
   switch (act) {
 #define VFX_TC_LAUNCH(A)                                                                                       \
   case A:                                                                                                      \
-    if (tf32) conv_gemm_tc_kernel<A, true><<<grid, 64 + 32 * (int)p.epi_warps, smem_bytes, st>>>(tmA, tmW, tmR, tmO, tmT, p);  \
-    else conv_gemm_tc_kernel<A, false><<<grid, 64 + 32 * (int)p.epi_warps, smem_bytes, st>>>(tmA, tmW, tmR, tmO, tmT, p);      \
+    if (tf32) conv_gemm_tc_kernel<A, true, false><<<grid, 64 + 32 * (int)p.epi_warps, smem_bytes, st>>>(tmA, tmW, tmR, tmO, tmT, p);       \
+    else if (fp16) conv_gemm_tc_kernel<A, false, true><<<grid, 64 + 32 * (int)p.epi_warps, smem_bytes, st>>>(tmA, tmW, tmR, tmO, tmT, p);  \
+    else conv_gemm_tc_kernel<A, false, false><<<grid, 64 + 32 * (int)p.epi_warps, smem_bytes, st>>>(tmA, tmW, tmR, tmO, tmT, p);           \
     break
     VFX_TC_LAUNCH(VFX_ACT_NONE); VFX_TC_LAUNCH(VFX_ACT_LRELU); VFX_TC_LAUNCH(VFX_ACT_ELU);
     VFX_TC_LAUNCH(VFX_ACT_LRELU_XSINX); VFX_TC_LAUNCH(VFX_ACT_SIGMOID);

@@ -333,6 +333,8 @@ int bn_act(int precision, const float* x, long long x_sB, long long ldx, int B, 
                           reinterpret_cast<T*>(y), y_sB, ldy)
   if (precision == VFX_PREC_BF16) {
     if (vec) VFX_BN_LAUNCH(bn_act_kernel, __nv_bfloat16); else VFX_BN_LAUNCH(bn_act_scalar_kernel, __nv_bfloat16);
+  } else if (precision == VFX_PREC_FP16) {
+    if (vec) VFX_BN_LAUNCH(bn_act_kernel, __half); else VFX_BN_LAUNCH(bn_act_scalar_kernel, __half);
   } else if (precision == VFX_PREC_TF32) {
     if (vec) VFX_BN_LAUNCH(bn_act_kernel, tf32_t); else VFX_BN_LAUNCH(bn_act_scalar_kernel, tf32_t);
   } else {
@@ -392,6 +394,8 @@ int voc_normalize(const float* mel, int B, int T, int Tc, int input_is_log, cons
   if (precision == VFX_PREC_BF16)
     voc_normalize_kernel<__nv_bfloat16><<<g, 256, 0, st>>>(mel, B, T, Tc, input_is_log, tab,
                                                            reinterpret_cast<__nv_bfloat16*>(cond));
+  else if (precision == VFX_PREC_FP16)
+    voc_normalize_kernel<__half><<<g, 256, 0, st>>>(mel, B, T, Tc, input_is_log, tab, reinterpret_cast<__half*>(cond));
   else if (precision == VFX_PREC_TF32)
     voc_normalize_kernel<tf32_t><<<g, 256, 0, st>>>(mel, B, T, Tc, input_is_log, tab, reinterpret_cast<tf32_t*>(cond));
   else
@@ -404,6 +408,8 @@ int voc_normalize(const float* mel, int B, int T, int Tc, int input_is_log, cons
 int cast_rows(const float* x, long long n, void* y, int precision, cudaStream_t st) {
   if (precision == VFX_PREC_BF16)
     cast_kernel<__nv_bfloat16><<<grid_for(n), 256, 0, st>>>(x, n, reinterpret_cast<__nv_bfloat16*>(y));
+  else if (precision == VFX_PREC_FP16)
+    cast_kernel<__half><<<grid_for(n), 256, 0, st>>>(x, n, reinterpret_cast<__half*>(y));
   else if (precision == VFX_PREC_TF32)
     cast_kernel<tf32_t><<<grid_for(n), 256, 0, st>>>(x, n, reinterpret_cast<tf32_t*>(y));
   else
@@ -415,7 +421,7 @@ int cast_rows(const float* x, long long n, void* y, int precision, cudaStream_t 
 int reflect_pad3(void* buf, int B, int L, int C, int precision, cudaStream_t st) {
   VFX_REQUIRE(L >= 4, "reflect_pad3: length %d too short for reflection pad 3", L);
   const int g = grid_for((long long)B * 6 * C);
-  if (precision == VFX_PREC_BF16)
+  if (precision == VFX_PREC_BF16 || precision == VFX_PREC_FP16)      // a 2-byte copy either way
     reflect_pad3_kernel<__nv_bfloat16><<<g, 256, 0, st>>>(reinterpret_cast<__nv_bfloat16*>(buf), B, L, C);
   else
     reflect_pad3_kernel<float><<<g, 256, 0, st>>>(reinterpret_cast<float*>(buf), B, L, C);

@@ -579,8 +579,9 @@ int vocoder_generator(Ctx& c, const void* cond, int B, int Tc, float* wav_out, i
     // ---- ResStack: 8 x (x + conv_k3_d1(lrelu(conv_k3_d3^i(lrelu(x))))), modules.py:550-576,592-595
     // bf16, width 64: each pair is ONE fused kernel (h stays on chip); the activated operand copy ping-pongs between
     // A0 and Hh because a pair reads it with a halo that neighbouring tiles would overwrite in place.
-    const bool fuse_pairs = prec == VFX_PREC_BF16 && c.e->use_tc &&
-                            ((c.e->fuse_pair && Co == 64) || (c.e->fuse_pair2 && Co == 128));
+    const bool is16 = prec == VFX_PREC_BF16 || prec == VFX_PREC_FP16;          // 2-byte operand modes share every kernel
+    const bool fuse_pairs = is16 && c.e->use_tc &&
+                            ((c.e->fuse_pair && Co == 64) || (c.e->fuse_pair2 && Co == 128 && prec == VFX_PREC_BF16));
     // tf32, width 64: the encoded stream ping-pongs between X and the (otherwise unused) operand buffer; 8 pairs end in X
     const bool fuse_tf32 = enc && c.e->fuse_pair2 && Co == 64 && j == 3;
     void* a_cur = A0; void* a_nxt = Hh;
@@ -611,7 +612,7 @@ int vocoder_generator(Ctx& c, const void* cond, int B, int Tc, float* wav_out, i
       if (fuse_pairs) {
         vfx_pair_desc pd;
         memset(&pd, 0, sizeof(pd));
-        pd.precision = VFX_PREC_BF16; pd.impl = Co == 64 ? 1 : 2;
+        pd.precision = prec; pd.impl = Co == 64 ? 1 : 2;
         pd.a = a_cur; pd.x = X; pd.dilation = dil; pd.B = B; pd.L = (int)Lout; pd.C = Co;
         pd.w1 = getw(c, p + ".c1.w", (size_t)3 * Co * Co, prec); pd.b1 = getf(c, p + ".c1.b", Co);
         pd.w2 = getw(c, p + ".c2.w", (size_t)3 * Co * Co, prec); pd.b2 = getf(c, p + ".c2.b", Co);
@@ -724,7 +725,7 @@ int vfx_version(void) { return 100; }
 
 int vfx_engine_create(vfx_engine** out, int device, int precision) {
   VFX_REQUIRE(out != nullptr, "engine_create: out is null");
-  VFX_REQUIRE(precision == VFX_PREC_FP32 || precision == VFX_PREC_BF16 || precision == VFX_PREC_TF32,
+  VFX_REQUIRE(precision == VFX_PREC_FP32 || precision == VFX_PREC_BF16 || precision == VFX_PREC_TF32 || precision == VFX_PREC_FP16,
               "engine_create: bad precision %d", precision);
   if (device == -1) {   // planning-only: weight-set validation and workspace sizing on a host without a GPU
     vfx_engine* e = new vfx_engine();
@@ -995,7 +996,8 @@ int vfx_hf_cut(vfx_engine* e, const float* wav, int B, int L, float ratio, float
 int vfx_conv_gemm(int precision, int impl, const vfx_conv_desc* d, void* stream) {
   VFX_REQUIRE(d, "conv_gemm: null descriptor");
   if (impl == 1) {
-    VFX_REQUIRE(precision == VFX_PREC_BF16 || precision == VFX_PREC_TF32, "conv_gemm: the tcgen05 implementation takes bf16 or tf32 operands");
+    VFX_REQUIRE(precision == VFX_PREC_BF16 || precision == VFX_PREC_TF32 || precision == VFX_PREC_FP16,
+                "conv_gemm: the tcgen05 implementation takes bf16, fp16 or tf32 operands");
     return conv_gemm_tc(precision, *d, (cudaStream_t)stream);
   }
   return conv_gemm_simt(precision, *d, (cudaStream_t)stream);
@@ -1005,6 +1007,7 @@ int vfx_resstack_pair(const vfx_pair_desc* d, void* stream) {
   VFX_REQUIRE(d, "resstack_pair: null descriptor");
   const bool tf32 = d->precision == VFX_PREC_TF32;
   const bool one_cta = d->impl == 1 || (d->impl == 0 && !tf32 && d->C == 64 && !d->x_out);
+  if (d->precision == VFX_PREC_FP16 && !one_cta) { set_error("resstack_pair: fp16 operands are supported by the one-CTA kernel (C = 64) only"); return VFX_ERR_UNSUPPORTED; }
   int r = one_cta ? ((tf32 || d->x_out) ? VFX_ERR_UNSUPPORTED : resstack_pair_tc(*d, (cudaStream_t)stream))
                   : resstack_pair2_tc(*d, (cudaStream_t)stream);
   if (r == VFX_ERR_UNSUPPORTED)

@@ -1,4 +1,4 @@
-// Fused ResStack pair on the 5th-gen tensor cores (sm_100a, bf16 operands, C = 64):
+// Fused ResStack pair on the 5th-gen tensor cores (sm_100a, 16-bit operands -- bf16 or fp16 --, C = 64):
 //
 //     x' = x + conv2_{k3,d=1}( lrelu_0.01( conv1_{k3,d}( lrelu_0.01(x) ) + b1 ) ) + b2
 //
@@ -70,7 +70,7 @@ struct PTileIter {
   __device__ __forceinline__ PTile coord() const { PTile t; t.b = b; t.p0 = it * PTILE; return t; }
 };
 
-template <int ACT>
+template <int ACT, bool FP16>
 __global__ void __launch_bounds__(P_THREADS, 1)
 resstack_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW1,
                      const __grid_constant__ CUtensorMap tmW2, const __grid_constant__ CUtensorMap tmR,
@@ -278,8 +278,7 @@ resstack_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
           for (int e = 0; e < 4; ++e) {
             float lo = f[2 * e], hi = f[2 * e + 1];
             lo = lo > 0.f ? lo : lo * 0.01f; hi = hi > 0.f ? hi : hi * 0.01f;
-            __nv_bfloat162 h2 = __floats2bfloat162_rn(inside ? lo : 0.f, inside ? hi : 0.f);
-            w[e] = *reinterpret_cast<uint32_t*>(&h2);
+            w[e] = pack16<FP16>(inside ? lo : 0.f, inside ? hi : 0.f);
           }
           *reinterpret_cast<uint4*>(hrow + (((uint32_t)(c * 4 + j) ^ swz) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
         }
@@ -353,12 +352,8 @@ resstack_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
           for (int j = 0; j < 4; ++j) {
             uint32_t w[4];
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              const float lo = act_fast<ACT>(f[8 * j + 2 * q], p.act_param);
-              const float hi = act_fast<ACT>(f[8 * j + 2 * q + 1], p.act_param);
-              __nv_bfloat162 h2 = __floats2bfloat162_rn(lo, hi);
-              w[q] = *reinterpret_cast<uint32_t*>(&h2);
-            }
+            for (int q = 0; q < 4; ++q)
+              w[q] = pack16<FP16>(act_fast<ACT>(f[8 * j + 2 * q], p.act_param), act_fast<ACT>(f[8 * j + 2 * q + 1], p.act_param));
             *reinterpret_cast<uint4*>(at + ((uint32_t)(j << 4) ^ sw64)) = make_uint4(w[0], w[1], w[2], w[3]);
           }
         }
@@ -417,8 +412,11 @@ int resstack_pair_tc(const vfx_pair_desc& d, cudaStream_t st) {
   p.has_raw = d.write_raw ? 1u : 0u; p.has_act = d.out_act ? 1u : 0u;
   p.act_param = d.act_param;
   p.epi_warp_bytes = 16384u + (d.out_act ? 4096u : 0u);
-  // c = F32, a = b = BF16, K-major, N = 64, M = 128
-  p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(PC >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+  // c = F32, a = b = BF16 (1) or F16 (0), K-major, N = 64, M = 128
+  const bool fp16 = d.precision == VFX_PREC_FP16;
+  const uint32_t fmt = fp16 ? 0u : 1u;
+  const CUtensorMapDataType op_dt = fp16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+  p.idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(PC >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
   // One box per tap by default: measured on B200 (tools/bench_pair.py, B = 32) the single halo box with row-shifted tap
   // views is SLOWER than three aligned 128-row boxes -- d = 1: 1.84 vs 1.72 ms, d = 27: 1.89 vs 1.68 ms (the L2 absorbs
   // the 3x operand re-reads; every MMA of conv1 then reads an 8-row-aligned tile).  VFX_PAIR_HALO=1 selects the halo box.
@@ -449,19 +447,19 @@ int resstack_pair_tc(const vfx_pair_desc& d, cudaStream_t st) {
     cuuint64_t strides[1] = {(cuuint64_t)PC * 2};
     cuuint32_t box[2] = {(cuuint32_t)PC, (cuuint32_t)PC};
     cuuint32_t es[2] = {1, 1};
-    return encode(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, es,
+    return encode(tm, op_dt, 2, const_cast<void*>(base), dims, strides, box, es,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   };
-  CUresult r = enc4(&tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, d.a, PC, p.halo ? p.halo_rows : 128u, CU_TENSOR_MAP_SWIZZLE_128B);
+  CUresult r = enc4(&tmA, op_dt, 2, d.a, PC, p.halo ? p.halo_rows : 128u, CU_TENSOR_MAP_SWIZZLE_128B);
   if (r == CUDA_SUCCESS) r = encw(&tmW1, d.w1);
   if (r == CUDA_SUCCESS) r = encw(&tmW2, d.w2);
   if (r == CUDA_SUCCESS) r = enc4(&tmR, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, d.x, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B);
   if (r == CUDA_SUCCESS) r = enc4(&tmO, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, d.x, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B);
   if (r == CUDA_SUCCESS) r = enc4(&tmO30, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, d.x, 32, 30, CU_TENSOR_MAP_SWIZZLE_128B);
   tmT = tmO; tmT30 = tmO30;
-  if (r == CUDA_SUCCESS && d.out_act) r = enc4(&tmT, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, d.out_act, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B);
-  if (r == CUDA_SUCCESS && d.out_act) r = enc4(&tmT30, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, d.out_act, 32, 30, CU_TENSOR_MAP_SWIZZLE_64B);
+  if (r == CUDA_SUCCESS && d.out_act) r = enc4(&tmT, op_dt, 2, d.out_act, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B);
+  if (r == CUDA_SUCCESS && d.out_act) r = enc4(&tmT30, op_dt, 2, d.out_act, 32, 30, CU_TENSOR_MAP_SWIZZLE_64B);
   if (r != CUDA_SUCCESS) { set_error("resstack_pair: cuTensorMapEncodeTiled failed with %d", (int)r); return VFX_ERR_CUDA; }
 
   int dev = 0, num_sms = 0;
@@ -470,7 +468,9 @@ int resstack_pair_tc(const vfx_pair_desc& d, cudaStream_t st) {
   if (dev < 64 && sms_of[dev]) num_sms = sms_of[dev];
   else {
     VFX_CUDA_CHECK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
-#define VFX_PAIR_ATTR(A) VFX_CUDA_CHECK(cudaFuncSetAttribute(resstack_pair_kernel<A>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024))
+#define VFX_PAIR_ATTR(A)                                                                                                          \
+  VFX_CUDA_CHECK(cudaFuncSetAttribute(resstack_pair_kernel<A, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); \
+  VFX_CUDA_CHECK(cudaFuncSetAttribute(resstack_pair_kernel<A, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024))
     VFX_PAIR_ATTR(VFX_ACT_NONE); VFX_PAIR_ATTR(VFX_ACT_LRELU); VFX_PAIR_ATTR(VFX_ACT_LRELU_XSINX);
 #undef VFX_PAIR_ATTR
     if (dev < 64) sms_of[dev] = num_sms;
@@ -479,8 +479,11 @@ int resstack_pair_tc(const vfx_pair_desc& d, cudaStream_t st) {
   p.d_it = grid % p.n_t; p.d_b = grid / p.n_t;
   const int act = d.out_act ? d.act : VFX_ACT_NONE;
   switch (act) {
-#define VFX_PAIR_LAUNCH(A) \
-  case A: resstack_pair_kernel<A><<<grid, P_THREADS, smem_bytes, st>>>(tmA, tmW1, tmW2, tmR, tmO, tmO30, tmT, tmT30, p); break
+#define VFX_PAIR_LAUNCH(A)                                                                                                 \
+  case A:                                                                                                                  \
+    if (fp16) resstack_pair_kernel<A, true><<<grid, P_THREADS, smem_bytes, st>>>(tmA, tmW1, tmW2, tmR, tmO, tmO30, tmT, tmT30, p);  \
+    else resstack_pair_kernel<A, false><<<grid, P_THREADS, smem_bytes, st>>>(tmA, tmW1, tmW2, tmR, tmO, tmO30, tmT, tmT30, p);      \
+    break
     VFX_PAIR_LAUNCH(VFX_ACT_NONE); VFX_PAIR_LAUNCH(VFX_ACT_LRELU); VFX_PAIR_LAUNCH(VFX_ACT_LRELU_XSINX);
 #undef VFX_PAIR_LAUNCH
     default: set_error("resstack_pair: unsupported activation %d", act); return VFX_ERR_INVALID;

@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <string>
@@ -38,11 +39,13 @@ static inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) 
 // ------------------------------------------------------------------ device helpers
 __device__ __forceinline__ float to_f(float v) { return v; }
 __device__ __forceinline__ float to_f(__nv_bfloat16 v) { return __bfloat162float(v); }
+__device__ __forceinline__ float to_f(__half v) { return __half2float(v); }
 template <typename T> __device__ __forceinline__ T from_f(float v);
 template <> __device__ __forceinline__ float from_f<float>(float v) { return v; }
 template <> __device__ __forceinline__ __nv_bfloat16 from_f<__nv_bfloat16>(float v) {
   return __float2bfloat16_rn(v);
 }
+template <> __device__ __forceinline__ __half from_f<__half>(float v) { return __float2half_rn(v); }
 // VFX_PREC_TF32 operand element: fp32 storage holding a value already rounded to tf32 (10-bit mantissa,
 // round-to-nearest) by its producer, so that the tensor core's truncation of the low 13 bits is exact.
 // (Un-rounded operands make kind::tf32 truncate: a CPU simulation of the whole path gave 1.4e-2 waveform
@@ -67,7 +70,13 @@ __device__ __forceinline__ float stream_dec(float s, float inv_slope) {
 }
 
 // element size of a GEMM operand / weight in the given vfx_precision
-static inline size_t prec_esz(int precision) { return precision == VFX_PREC_BF16 ? 2 : 4; }
+static inline size_t prec_esz(int precision) { return (precision == VFX_PREC_BF16 || precision == VFX_PREC_FP16) ? 2 : 4; }
+// two fp32 -> one packed pair of 16-bit operands (bf16 or fp16), round-to-nearest
+template <bool FP16> __device__ __forceinline__ uint32_t pack16(float lo, float hi) {
+  if (FP16) { __half2 h = __floats2half2_rn(lo, hi); return *reinterpret_cast<uint32_t*>(&h); }
+  __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
 
 __device__ __forceinline__ float apply_act(float v, int act, float p) {
   switch (act) {

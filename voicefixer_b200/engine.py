@@ -25,7 +25,8 @@ def default_precision():
     """"tf32": tcgen05 kind::tf32 on tf32-rounded fp32 operands -- the arithmetic class of the reference's own CUDA path
     (cuDNN TF32 convolutions; waveform within 2e-3 relative RMS of the fp32 CPU path).  VFX_PRECISION selects another mode:
     "bf16" (tcgen05 kind::f16, 1.6x faster, 1.3e-2 relative RMS / 2.7e-3 mean-abs: inside the reference's own 1e-2 mean-abs
-    acceptance bar) or "fp32" (SIMT fp32 validation path, reference-exact to ~4e-6)."""
+    acceptance bar), "fp16" (tcgen05 kind::f16 on fp16 operands: tf32's 10-bit mantissa, hence tf32's parity, at the bf16 mode's
+    speed -- within fp16's exponent range) or "fp32" (SIMT fp32 validation path, reference-exact to ~4e-6)."""
     return os.environ.get("VFX_PRECISION", "tf32")
 
 

@@ -22,7 +22,7 @@ class _Wdt:
     """Weight element format of a vfx_precision: storage dtype + rounding + whether tiny Cin is padded for the MMA."""
 
     def __init__(self, precision):
-        if precision not in ("fp32", "bf16", "tf32"):
+        if precision not in ("fp32", "bf16", "tf32", "fp16"):
             raise ValueError(f"unknown precision '{precision}'")
         self.precision = precision
         self.tensor_core = precision != "fp32"
@@ -32,6 +32,10 @@ class _Wdt:
             return t.to(torch.bfloat16)
         if self.precision == "tf32":
             return round_tf32(t)
+        if self.precision == "fp16":
+            if float(t.abs().max()) > 6.0e4:
+                raise ValueError("a weight exceeds fp16's range (65504): use precision tf32 or bf16 for this checkpoint")
+            return t.to(torch.float16)
         return t.float()
 
 
