@@ -30,7 +30,7 @@ def samples_in(path):
 
 
 @pytest.mark.timeout(600)
-@pytest.mark.parametrize("precision", ["fp32", "tf32", "bf16"])
+@pytest.mark.parametrize("precision", ["fp32", "tf32", "fp16", "bf16"])
 def test_reference_acceptance_script(tmp_path, monkeypatch, states, precision):
     import torch
     from voicefixer import VoiceFixer, Vocoder                       # test/test.py:22
