@@ -78,3 +78,39 @@ def test_restore_stream_matches_segmentwise_restore(home):
     assert streamed.shape == whole.shape and rel_rms(streamed, whole) < 1e-6
     short = np.concatenate(list(vf.restore_stream(blocks[:12], chunk_seconds=1.0, context_seconds=0.5)))
     assert short.shape[0] == sum(len(b) for b in blocks[:12]) and np.isfinite(short).all()
+
+
+def test_too_small_workspace_is_refused_before_any_launch(states):
+    """C ABI: a workspace smaller than the call needs returns VFX_ERR_WORKSPACE up front (no launch, nothing written)."""
+    import ctypes
+    import torch
+    from voicefixer_b200 import _lib, synthetic
+    from voicefixer_b200.engine import Engine
+    eng = Engine(states[0], states[1], precision="tf32")
+    wav = torch.from_numpy(synthetic.make_utterances(1, seconds=0.5, seed=3)).cuda()
+    out = torch.full_like(wav, 7.0)
+    need = eng.workspace_bytes(1, wav.shape[1])
+    ws = torch.zeros(need // 4, dtype=torch.uint8, device="cuda")
+    guard = torch.zeros(1 << 20, dtype=torch.uint8, device="cuda")          # whatever sits behind a too-small buffer
+    launches = eng.launch_count()
+    p = lambda t: ctypes.c_void_p(t.data_ptr())
+    rc = eng.lib.vfx_restore(eng.h, p(wav), 1, wav.shape[1], 0, None, p(out), p(ws), ws.numel(), None)
+    torch.cuda.synchronize()
+    assert rc == -3 and b"workspace too small" in eng.lib.vfx_last_error()
+    assert eng.launch_count() == launches and float(out.min()) == 7.0 and int(guard.max()) == 0
+    y = eng.restore(wav)                                                     # the engine is still usable
+    assert bool(torch.isfinite(y).all())
+
+
+@pytest.mark.timeout(600)
+def test_long_recordings_are_chunked(home, monkeypatch):
+    """restore_inmem batches the 30 s segments in chunks sized to the free memory; chunk size 1 (the reference's
+    one-at-a-time walk) gives the same result as one batch."""
+    from voicefixer_b200 import synthetic, api
+    vf = api.VoiceFixer(precision="tf32")
+    wav = np.tile(synthetic.make_utterances(1, seconds=6.0, seed=83)[0], 11)[: 44100 * 61]      # three segments
+    assert vf._engine.max_batch(44100 * 30) >= 1
+    whole = vf.restore_inmem(wav, cuda=True, mode=0)
+    monkeypatch.setattr(vf._engine, "max_batch", lambda L, cap=64, reserve=0: 1)
+    one_by_one = vf.restore_inmem(wav, cuda=True, mode=0)
+    assert whole.shape == one_by_one.shape == (1, wav.shape[0]) and rel_rms(one_by_one, whole) < 1e-6
