@@ -64,7 +64,8 @@ int vfx_engine_set_tensor(vfx_engine* e, const char* name, const void* dev_ptr, 
  * "profile" (0/1/2, see vfx_profile_report; 2 = one tag per shape / dilation),
  * "fuse_pair" (BF16: width-64 ResStack pairs as one fused kernel, default 1),
  * "tf32_stream" (TF32: vocoder residual streams as one encoded tensor, vfx_conv_desc.res_enc / raw_enc, default 1),
- * "fuse_pair2" (two-CTA cluster pipeline for BF16 width 128 / TF32 width 64 pairs: correct but slower, default 0). */
+ * "fuse_pair2" (two-CTA cluster pipeline: 1 [default] = BF16 / FP16 width-128 ResStack pairs, 2 = also TF32 width 64 [no gain],
+ *  0 = off). */
 int vfx_engine_set_option(vfx_engine* e, const char* key, int value);
 /* Number of CUDA kernels this library has launched in this process (bench.py's gpu_launches). */
 unsigned long long vfx_launch_count(void);
@@ -174,8 +175,8 @@ int vfx_conv_gemm(int precision, int impl, const vfx_conv_desc* d, void* stream)
  *   x' = x + conv2_{k3,d=1}( lrelu_0.01( conv1_{k3,dilation}( a ) + b1 ) ) + b2
  * ResStack.forward voicefixer/vocoder/model/modules.py:592-595 (layers :550-576).  The intermediate never leaves the chip.
  * Two implementations (impl: 0 = pick, 1 = one CTA per tile, 2 = two-CTA cluster pipeline: conv1 on one SM, conv2 on its
- * neighbour, the intermediate crossing through distributed shared memory):
- *   VFX_PREC_BF16, C = 64 (impl 1 or 2), C = 128 (impl 2): a = lrelu_0.01(x) as bf16 [B][L][C]; x fp32 is read as the residual
+ * neighbour, the intermediate crossing through an L2-resident scratch ring):
+ *   VFX_PREC_BF16 / VFX_PREC_FP16, C = 64 (impl 1), C = 128 (impl 2): a = lrelu_0.01(x) in the operand format [B][L][C]; x fp32 is read as the residual
  *     and, if write_raw, overwritten with x' (or written to x_out); out_act (optional, bf16, must not alias a) receives act(x').
  *   VFX_PREC_TF32, C = 64 (impl 2), stream_enc = 1: a == x == the encoded stream S (vfx_conv_desc.raw_enc), fp32 [B][L][C];
  *     the result goes to x_out (required, aliasing neither input) as S' (stream_enc_out = 1) or as plain x' (0).
@@ -192,7 +193,10 @@ typedef struct vfx_pair_desc {
   int impl;
   float* x_out;             /* NULL = in place over x (bf16 only) */
   int stream_enc, stream_enc_out;
+  void* scratch;            /* impl 2: device scratch of vfx_resstack_pair_scratch_bytes() bytes, 128-byte aligned (the */
+  size_t scratch_bytes;     /* intermediate tile crosses from one SM to its neighbour through it; stays in L2)          */
 } vfx_pair_desc;
+size_t vfx_resstack_pair_scratch_bytes(void);
 int vfx_resstack_pair(const vfx_pair_desc* d, void* stream);
 
 /* One direction-pair GRU layer recurrence: gi[B][T][2][768] (x W_ih^T + b_ih, fwd|bwd),

@@ -108,35 +108,61 @@ def test_pair_rejects_other_widths():
 
 
 # ---------------------------------------------------------------------------- two-CTA cluster pipeline (impl = 2)
+def test_pair2_needs_scratch():
+    from voicefixer_b200 import _lib
+    from voicefixer_b200._lib import VfxError
+    lib = _lib.load()
+    x = _rnd(1, 300, 128, seed=1)
+    a = x.bfloat16()
+    w = _rnd(3, 128, 128, seed=2).bfloat16()
+    b = _rnd(128, seed=3)
+    act = torch.zeros_like(a)
+    d = _lib.PairDesc()
+    d.a, d.x, d.w1, d.b1, d.dilation, d.w2, d.b2 = a.data_ptr(), x.data_ptr(), w.data_ptr(), b.data_ptr(), 1, w.data_ptr(), b.data_ptr()
+    d.B, d.L, d.C, d.write_raw, d.out_act, d.act, d.act_param, d.precision, d.impl = 1, 300, 128, 1, act.data_ptr(), 1, 0.01, 1, 2
+    with pytest.raises(VfxError, match="scratch"):
+        _lib.check(lib.vfx_resstack_pair(ctypes.byref(d), None), "pair2")
+
+
+_SCRATCH = {}
+
+
 def _desc(lib_mod, **kw):
     d = lib_mod.PairDesc()
     for k, v in kw.items():
         setattr(d, k, v)
+    if kw.get("impl") == 2:                 # the two-CTA pipeline hands the intermediate tile over through this scratch ring
+        n = int(lib_mod.load().vfx_resstack_pair_scratch_bytes())
+        if "buf" not in _SCRATCH:
+            _SCRATCH["buf"] = torch.empty(n, dtype=torch.uint8, device=DEV)
+        d.scratch, d.scratch_bytes = _SCRATCH["buf"].data_ptr(), n
     return d
 
 
+@pytest.mark.parametrize("prec", ["bf16", "fp16"])
 @pytest.mark.parametrize("C,L,dil,B", [(128, 1000, 1, 2), (128, 5000, 27, 1), (128, 700, 243, 2), (128, 20000, 9, 3),
                                        (128, 9000, 2187, 1), (128, 125, 1, 1)])
-def test_pair2_bf16_matches_two_convolutions(C, L, dil, B):
-    """conv1 on one SM, conv2 on its cluster neighbour, h through distributed shared memory: same arithmetic as impl 1."""
+def test_pair2_16bit_matches_two_convolutions(C, L, dil, B, prec):
+    """conv1 on one SM, conv2 on its cluster neighbour, h through the L2-resident scratch ring: same arithmetic as impl 1."""
     from voicefixer_b200 import _lib
     lib = _lib.load()
     torch.backends.cudnn.allow_tf32 = False
+    dt = torch.bfloat16 if prec == "bf16" else torch.float16
     x = _rnd(B, L, C, seed=1)
-    a = F.leaky_relu(x, 0.01).bfloat16()
-    w1, w2 = _rnd(C, C, 3, seed=2, scale=0.06).bfloat16(), _rnd(C, C, 3, seed=3, scale=0.06).bfloat16()
+    a = F.leaky_relu(x, 0.01).to(dt)
+    w1, w2 = _rnd(C, C, 3, seed=2, scale=0.06).to(dt), _rnd(C, C, 3, seed=3, scale=0.06).to(dt)
     b1, b2 = _rnd(C, seed=4, scale=0.1), _rnd(C, seed=5, scale=0.1)
     ref = _ref(x, a, w1, b1, w2, b2, dil)
     xin = x.clone()
     w1p, w2p = w1.permute(2, 0, 1).contiguous(), w2.permute(2, 0, 1).contiguous()
-    act = torch.zeros(B, L, C, device=DEV, dtype=torch.bfloat16)
+    act = torch.zeros(B, L, C, device=DEV, dtype=dt)
     d = _desc(_lib, a=a.data_ptr(), x=xin.data_ptr(), w1=w1p.data_ptr(), b1=b1.data_ptr(), dilation=dil, w2=w2p.data_ptr(),
               b2=b2.data_ptr(), B=B, L=L, C=C, write_raw=1, out_act=act.data_ptr(), act=_lib.ACT["lrelu"], act_param=0.01,
-              precision=_lib.PREC["bf16"], impl=2)
+              precision=_lib.PREC[prec], impl=2)
     _lib.check(lib.vfx_resstack_pair(ctypes.byref(d), ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)), "pair2")
     torch.cuda.synchronize()
     assert rel_rms((xin - x).cpu(), (ref - x).cpu()) < 1e-4
-    assert rel_rms(act.float().cpu(), F.leaky_relu(ref, 0.01).cpu()) < 4e-3
+    assert rel_rms(act.float().cpu(), F.leaky_relu(ref, 0.01).cpu()) < (4e-3 if prec == "bf16" else 5e-4)
 
 
 def _enc(x, slope=0.01):

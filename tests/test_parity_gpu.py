@@ -273,7 +273,7 @@ def test_tf32_encoded_stream_engine_path(states, oracle_10s):
     assert rel_rms(y1, y0) < FULL_TOL["tf32"][0]
 
 
-@pytest.mark.parametrize("prec", ["tf32", "bf16"])
+@pytest.mark.parametrize("prec", ["tf32", "fp16", "bf16"])
 def test_two_cta_pair_pipeline_engine_path(states, oracle_10s, prec):
     """fuse_pair2: ResStack pairs as a two-CTA cluster pipeline (bf16 width 128, tf32 width 64): same tolerance as the
     mode's plain path, and within rounding noise of it."""
@@ -282,7 +282,7 @@ def test_two_cta_pair_pipeline_engine_path(states, oracle_10s, prec):
     eng = Engine(states[0], states[1], precision=prec)
     eng.set_option("fuse_pair2", 0)
     y0 = eng.restore(wav[None]).cpu().numpy()
-    eng.set_option("fuse_pair2", 1)
+    eng.set_option("fuse_pair2", 2)
     y1 = eng.restore(wav[None]).cpu().numpy()
     assert rel_rms(y1, ref) < FULL_TOL[prec][0] and float(np.mean(np.abs(y1 - ref))) < FULL_TOL[prec][1]
     assert rel_rms(y1, y0) < FULL_TOL[prec][0]

@@ -27,11 +27,13 @@ w1 = (torch.randn(3, C, C, device=dev) * 0.05).to(odt)
 w2 = (torch.randn(3, C, C, device=dev) * 0.05).to(odt)
 b1, b2 = torch.randn(C, device=dev) * 0.1, torch.randn(C, device=dev) * 0.1
 st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+scratch = torch.empty(int(lib.vfx_resstack_pair_scratch_bytes()), dtype=torch.uint8, device=dev)
 for dil in [int(v) for v in args.dil.split(",")]:
     d = _lib.PairDesc()
     d.a, d.x, d.w1, d.b1, d.dilation, d.w2, d.b2 = a.data_ptr(), x.data_ptr(), w1.data_ptr(), b1.data_ptr(), dil, w2.data_ptr(), b2.data_ptr()
     d.B, d.L, d.C, d.write_raw, d.act, d.act_param = B, L, C, 1, _lib.ACT["lrelu"], 0.01
     d.precision, d.impl = _lib.PREC[args.prec], args.impl
+    d.scratch, d.scratch_bytes = scratch.data_ptr(), scratch.numel()
     if tf32:
         d.x_out, d.stream_enc, d.stream_enc_out = a2.data_ptr(), 1, 1
     else:

@@ -37,7 +37,8 @@ class PairDesc(ctypes.Structure):
     """struct vfx_pair_desc (include/vfx_b200.h)."""
     _fields_ = [("a", _vp), ("x", _vp), ("w1", _vp), ("b1", _vp), ("dilation", _i), ("w2", _vp), ("b2", _vp),
                 ("B", _i), ("L", _i), ("C", _i), ("write_raw", _i), ("out_act", _vp), ("act", _i), ("act_param", _f),
-                ("precision", _i), ("impl", _i), ("x_out", _vp), ("stream_enc", _i), ("stream_enc_out", _i)]
+                ("precision", _i), ("impl", _i), ("x_out", _vp), ("stream_enc", _i), ("stream_enc_out", _i),
+                ("scratch", _vp), ("scratch_bytes", _sz)]
 
 
 # name -> (restype, argtypes); must list every symbol include/vfx_b200.h declares
@@ -61,6 +62,7 @@ SIGNATURES = {
     "vfx_hf_cut": (_i, [_vp, _vp, _i, _i, _f, _vp, _vp, _vp, _sz, _vp]),
     "vfx_conv_gemm": (_i, [_i, _i, _c.POINTER(ConvDesc), _vp]),
     "vfx_resstack_pair": (_i, [_c.POINTER(PairDesc), _vp]),
+    "vfx_resstack_pair_scratch_bytes": (_sz, []),
     "vfx_gru_layer": (_i, [_vp, _vp, _vp, _i, _i, _vp, _vp]),
 }
 

@@ -44,7 +44,7 @@ struct vfx_engine {
   int parts = 0;    // VFX_PART_* bits of the weight sets found complete by vfx_engine_finalize
   int tf32_stream = 1;  // TF32: vocoder residual streams are kept as ONE encoded fp32 tensor (operand + residual carrier)
   int fuse_pair = 1;  // BF16: ResStack pairs of width 64 run as ONE fused kernel (resstack_pair_tc.cu)
-  int fuse_pair2 = 0; // two-CTA cluster pipeline (resstack_pair2_tc.cu): BF16 width 128, TF32 width 64 (encoded stream)
+  int fuse_pair2 = 1; // two-CTA cluster pipeline (resstack_pair2_tc.cu): 1 = BF16 / FP16 width 128; 2 = also TF32 width 64 (no gain)
   int profile = 0;
   std::vector<vfx::ProfRec> prof;
   std::string prof_report;
@@ -581,11 +581,13 @@ int vocoder_generator(Ctx& c, const void* cond, int B, int Tc, float* wav_out, i
     // A0 and Hh because a pair reads it with a halo that neighbouring tiles would overwrite in place.
     const bool is16 = prec == VFX_PREC_BF16 || prec == VFX_PREC_FP16;          // 2-byte operand modes share every kernel
     const bool fuse_pairs = is16 && c.e->use_tc &&
-                            ((c.e->fuse_pair && Co == 64) || (c.e->fuse_pair2 && Co == 128 && prec == VFX_PREC_BF16));
+                            ((c.e->fuse_pair && Co == 64) || (c.e->fuse_pair2 && Co == 128));
     // tf32, width 64: the encoded stream ping-pongs between X and the (otherwise unused) operand buffer; 8 pairs end in X
-    const bool fuse_tf32 = enc && c.e->fuse_pair2 && Co == 64 && j == 3;
+    const bool fuse_tf32 = enc && c.e->fuse_pair2 >= 2 && Co == 64 && j == 3;
     void* a_cur = A0; void* a_nxt = Hh;
     float* s_cur = X; float* s_nxt = (float*)A0;
+    void* pair_scratch = nullptr;                       // two-CTA pipeline: the h tiles cross SMs through this (L2-resident) ring
+    if (fuse_tf32 || (fuse_pairs && Co == 128)) pair_scratch = c.ws->raw(resstack_pair2_scratch_bytes());
     int dil = 1;
     for (int i = 0; i < 8; ++i, dil *= 3) {
       snprintf(name, sizeof(name), "voc.rs%d.l%d", j, i);
@@ -597,6 +599,7 @@ int vocoder_generator(Ctx& c, const void* cond, int B, int Tc, float* wav_out, i
         pd.w1 = getw(c, p + ".c1.w", (size_t)3 * Co * Co, prec); pd.b1 = getf(c, p + ".c1.b", Co);
         pd.w2 = getw(c, p + ".c2.w", (size_t)3 * Co * Co, prec); pd.b2 = getf(c, p + ".c2.b", Co);
         pd.write_raw = 1; pd.precision = VFX_PREC_TF32; pd.impl = 2;
+        pd.scratch = pair_scratch; pd.scratch_bytes = resstack_pair2_scratch_bytes();
         pd.stream_enc = 1; pd.stream_enc_out = i < 7 ? 1 : 0;     // the last pair hands plain x' to the final convolution
         if (!c.dry && c.rc == VFX_OK) {
           char pt[48], ptd[64];
@@ -613,6 +616,7 @@ int vocoder_generator(Ctx& c, const void* cond, int B, int Tc, float* wav_out, i
         vfx_pair_desc pd;
         memset(&pd, 0, sizeof(pd));
         pd.precision = prec; pd.impl = Co == 64 ? 1 : 2;
+        pd.scratch = pair_scratch; pd.scratch_bytes = resstack_pair2_scratch_bytes();
         pd.a = a_cur; pd.x = X; pd.dilation = dil; pd.B = B; pd.L = (int)Lout; pd.C = Co;
         pd.w1 = getw(c, p + ".c1.w", (size_t)3 * Co * Co, prec); pd.b1 = getf(c, p + ".c1.b", Co);
         pd.w2 = getw(c, p + ".c2.w", (size_t)3 * Co * Co, prec); pd.b2 = getf(c, p + ".c2.b", Co);
@@ -1003,11 +1007,12 @@ int vfx_conv_gemm(int precision, int impl, const vfx_conv_desc* d, void* stream)
   return conv_gemm_simt(precision, *d, (cudaStream_t)stream);
 }
 
+size_t vfx_resstack_pair_scratch_bytes(void) { return resstack_pair2_scratch_bytes(); }
+
 int vfx_resstack_pair(const vfx_pair_desc* d, void* stream) {
   VFX_REQUIRE(d, "resstack_pair: null descriptor");
   const bool tf32 = d->precision == VFX_PREC_TF32;
   const bool one_cta = d->impl == 1 || (d->impl == 0 && !tf32 && d->C == 64 && !d->x_out);
-  if (d->precision == VFX_PREC_FP16 && !one_cta) { set_error("resstack_pair: fp16 operands are supported by the one-CTA kernel (C = 64) only"); return VFX_ERR_UNSUPPORTED; }
   int r = one_cta ? ((tf32 || d->x_out) ? VFX_ERR_UNSUPPORTED : resstack_pair_tc(*d, (cudaStream_t)stream))
                   : resstack_pair2_tc(*d, (cudaStream_t)stream);
   if (r == VFX_ERR_UNSUPPORTED)

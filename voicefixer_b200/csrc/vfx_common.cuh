@@ -94,7 +94,8 @@ __device__ __forceinline__ float apply_act(float v, int act, float p) {
 // ------------------------------------------------------------------ kernels (host launchers)
 int conv_gemm_simt(int precision, const vfx_conv_desc& d, cudaStream_t st);
 int resstack_pair_tc(const vfx_pair_desc& d, cudaStream_t st);     // fused ResStack pair (bf16, C = 64), one CTA per tile
-int resstack_pair2_tc(const vfx_pair_desc& d, cudaStream_t st);    // ... two-CTA cluster pipeline (bf16 C = 64 / 128, tf32 C = 64)
+int resstack_pair2_tc(const vfx_pair_desc& d, cudaStream_t st);    // ... two-CTA cluster pipeline (bf16 C = 128, tf32 C = 64)
+size_t resstack_pair2_scratch_bytes();
 int conv_gemm_tc(int precision, const vfx_conv_desc& d, cudaStream_t st);   // tcgen05: bf16 (kind::f16) or tf32 (kind::tf32)
 
 // y = act(scale[b][c]*x + shift[b][c]); x fp32 [B][P][C] (row pitch ldx), y operand type.
