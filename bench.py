@@ -323,7 +323,9 @@ def roofline_from(rep, B, L_by_stack, precision, peaks, peaks_src, tot_ms):
         c1, c2 = rep.get(f"voc.rs{j}.c1"), rep.get(f"voc.rs{j}.c2")
         if fused:
             ms_pair, n = fused["ms"] / fused["count"], fused["count"]
-            kern = f"{'resstack_pair_kernel' if C == 64 and precision != 'tf32' else 'resstack_pair2_kernel (two-CTA cluster)'} [voc.rs{j}.pair]"
+            kname = ("resstack_pair3_kernel (one SM, residual stashed in TMEM)" if precision == "tf32" and C == 64
+                     else "resstack_pair_kernel" if C == 64 else "resstack_pair2_kernel (two-CTA cluster)")
+            kern = f"{kname} [voc.rs{j}.pair]"
             flops, model_bytes = fused["flops"] / fused["count"], fused["bytes"] / fused["count"]
         elif c1 and c2:
             ms_pair, n = (c1["ms"] + c2["ms"]) / c2["count"], c2["count"]

@@ -175,10 +175,15 @@ def _dec(s, slope=0.01):
     return torch.where(y > 0, y, y / slope)
 
 
-@pytest.mark.parametrize("L,dil,B,enc_out", [(1000, 1, 2, 1), (5000, 81, 1, 1), (3000, 9, 2, 0), (20000, 729, 2, 1)])
-def test_pair2_tf32_encoded_stream(L, dil, B, enc_out):
+@pytest.mark.parametrize("impl", [3, 2])
+@pytest.mark.parametrize("L,dil,B,enc_out", [(1000, 1, 2, 1), (5000, 81, 1, 1), (3000, 9, 2, 0), (20000, 729, 2, 1),
+                                             (125, 1, 1, 1), (127, 3, 2, 0), (4000, 27, 1, 1), (9000, 2187, 1, 1),
+                                             (40000, 243, 3, 1), (378, 9, 1, 1)])
+def test_pair_tf32_encoded_stream(L, dil, B, enc_out, impl):
     """tf32, C = 64: the encoded stream S is operand and residual carrier; the result goes to the other buffer as S' (or as
-    plain x' for the last pair of a stack).  Reference: tf32-rounded operands and intermediate, fp32 accumulation."""
+    plain x' for the last pair of a stack).  impl 3 = one SM, residual stashed in tensor memory (resstack_pair3_tc.cu: halo
+    boxes for d <= 9, aligned boxes beyond); impl 2 = the two-CTA pipeline.  Reference: tf32-rounded operands and
+    intermediate, fp32 accumulation."""
     from voicefixer_b200 import _lib
     from voicefixer_b200.weights import round_tf32
     lib = _lib.load()
@@ -195,7 +200,7 @@ def test_pair2_tf32_encoded_stream(L, dil, B, enc_out):
     out = torch.zeros_like(S)
     w1p, w2p = w1.permute(2, 0, 1).contiguous(), w2.permute(2, 0, 1).contiguous()
     d = _desc(_lib, a=S.data_ptr(), x=S.data_ptr(), w1=w1p.data_ptr(), b1=b1.data_ptr(), dilation=dil, w2=w2p.data_ptr(),
-              b2=b2.data_ptr(), B=B, L=L, C=C, write_raw=1, precision=_lib.PREC["tf32"], impl=2, x_out=out.data_ptr(),
+              b2=b2.data_ptr(), B=B, L=L, C=C, write_raw=1, precision=_lib.PREC["tf32"], impl=impl, x_out=out.data_ptr(),
               stream_enc=1, stream_enc_out=enc_out)
     keep = S.clone()
     _lib.check(lib.vfx_resstack_pair(ctypes.byref(d), ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)), "pair2")

@@ -280,12 +280,28 @@ def test_two_cta_pair_pipeline_engine_path(states, oracle_10s, prec):
     from voicefixer_b200.engine import Engine
     wav, ref = oracle_10s
     eng = Engine(states[0], states[1], precision=prec)
+    eng.set_option("fuse_pair3", 0)                       # tf32 width 64 would otherwise take the one-SM fused kernel
     eng.set_option("fuse_pair2", 0)
     y0 = eng.restore(wav[None]).cpu().numpy()
     eng.set_option("fuse_pair2", 2)
     y1 = eng.restore(wav[None]).cpu().numpy()
     assert rel_rms(y1, ref) < FULL_TOL[prec][0] and float(np.mean(np.abs(y1 - ref))) < FULL_TOL[prec][1]
     assert rel_rms(y1, y0) < FULL_TOL[prec][0]
+
+
+def test_tf32_fused_pair_engine_path(states, oracle_10s):
+    """fuse_pair3 (default on): the width-64 ResStack pairs of the tf32 mode as one fused kernel each (h on chip, residual
+    stashed in tensor memory): same arithmetic as the two-launch path -- the outputs agree to rounding noise of the
+    accumulation order, far inside the mode's tolerance."""
+    from voicefixer_b200.engine import Engine
+    wav, ref = oracle_10s
+    eng = Engine(states[0], states[1], precision="tf32")
+    eng.set_option("fuse_pair3", 0)
+    y0 = eng.restore(wav[None]).cpu().numpy()
+    eng.set_option("fuse_pair3", 1)
+    y1 = eng.restore(wav[None]).cpu().numpy()
+    assert rel_rms(y1, ref) < FULL_TOL["tf32"][0] and float(np.mean(np.abs(y1 - ref))) < FULL_TOL["tf32"][1]
+    assert rel_rms(y1, y0) < 5e-4
 
 
 # ---------------------------------------------------------------------------- fp16 tensor-core path

@@ -11,7 +11,7 @@ ap.add_argument("--B", type=int, default=32)
 ap.add_argument("--L", type=int, default=443646)
 ap.add_argument("--dil", default="1,3,9,27,81,243,729,2187")
 ap.add_argument("--iters", type=int, default=5)
-ap.add_argument("--impl", type=int, default=0, help="0 = pick, 1 = one CTA per tile, 2 = two-CTA cluster pipeline")
+ap.add_argument("--impl", type=int, default=0, help="0 = pick, 1 = one CTA per tile (16-bit), 2 = two-CTA cluster pipeline, 3 = one CTA per tile, tf32 (TMEM residual stash)")
 ap.add_argument("--C", type=int, default=64)
 ap.add_argument("--prec", default="bf16")
 args = ap.parse_args()

@@ -5,7 +5,7 @@ import collections, csv, io, os, re, shutil, subprocess, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 os.chdir(ROOT)
 head = subprocess.run(["git", "rev-parse", "--short", "HEAD"], capture_output=True, text=True).stdout.strip()
-for n in ("pair_c64", "pair2_c128", "rs2", "unet_c32", "gru", "voc_post", "rs3_tf32"):
+for n in ("pair_c64", "pair2_c128", "rs2", "unet_c32", "gru", "voc_post", "rs3_tf32", "pair3_tf32"):
     subprocess.run([sys.executable, "tools/ncu_summary.py", f"gpurun_out/r02_{n}.ncu-rep", f"profiles/r02_{n}.txt",
                     f"round 2, captured from the sources of commit {head}, B=32 (tools/capture_r02.sh)"], capture_output=True)
 for P in ("bf16", "tf32"):
@@ -32,9 +32,9 @@ if os.path.exists("profiles/ncu_traffic.json"):
 subprocess.run([sys.executable, "tools/update_traffic.py", "gpurun_out/r02_pair_c64.ncu-rep", "bf16:voc.rs3.pair:B32", "1",
                 "profiles/r02_pair_c64.txt (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum per fused pair launch)",
                 "resstack_pair_tc.cu,tc_ptx.cuh,vfx_common.cuh"], check=True)
-subprocess.run([sys.executable, "tools/update_traffic.py", "gpurun_out/r02_rs3_tf32.ncu-rep", "tf32:voc.rs3.pair:B32", "2",
-                "profiles/r02_rs3_tf32.txt (ncu --set full): conv1 launch + encoded-stream conv2 launch of one C = 64 pair",
-                "conv_gemm_tc.cu,tc_ptx.cuh,vfx_common.cuh", "0,2"], check=True)
+subprocess.run([sys.executable, "tools/update_traffic.py", "gpurun_out/r02_pair3_tf32.ncu-rep", "tf32:voc.rs3.pair:B32", "1",
+                "profiles/r02_pair3_tf32.txt (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum per fused tf32 pair launch)",
+                "resstack_pair3_tc.cu,tc_ptx.cuh,vfx_common.cuh"], check=True)
 subprocess.run([sys.executable, "tools/update_traffic.py", "gpurun_out/r02_pair2_c128.ncu-rep", "bf16:voc.rs2.pair:B32", "1",
                 "profiles/r02_pair2_c128.txt (ncu --set full): one launch of the two-CTA pipelined C = 128 pair",
                 "resstack_pair2_tc.cu,tc_ptx.cuh,vfx_common.cuh"], check=True)

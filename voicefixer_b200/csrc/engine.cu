@@ -44,6 +44,7 @@ struct vfx_engine {
   int parts = 0;    // VFX_PART_* bits of the weight sets found complete by vfx_engine_finalize
   int tf32_stream = 1;  // TF32: vocoder residual streams are kept as ONE encoded fp32 tensor (operand + residual carrier)
   int fuse_pair = 1;  // BF16: ResStack pairs of width 64 run as ONE fused kernel (resstack_pair_tc.cu)
+  int fuse_pair3 = 1; // TF32 width 64: one-SM fused pair with the residual stashed in tensor memory (resstack_pair3_tc.cu)
   int fuse_pair2 = 1; // two-CTA cluster pipeline (resstack_pair2_tc.cu): 1 = BF16 / FP16 width 128; 2 = also TF32 width 64 (no gain)
   int profile = 0;
   std::vector<vfx::ProfRec> prof;
@@ -583,11 +584,12 @@ int vocoder_generator(Ctx& c, const void* cond, int B, int Tc, float* wav_out, i
     const bool fuse_pairs = is16 && c.e->use_tc &&
                             ((c.e->fuse_pair && Co == 64) || (c.e->fuse_pair2 && Co == 128));
     // tf32, width 64: the encoded stream ping-pongs between X and the (otherwise unused) operand buffer; 8 pairs end in X
-    const bool fuse_tf32 = enc && c.e->fuse_pair2 >= 2 && Co == 64 && j == 3;
+    const bool fuse_tf32 = enc && (c.e->fuse_pair3 || c.e->fuse_pair2 >= 2) && Co == 64 && j == 3;
+    const int tf32_impl = c.e->fuse_pair3 ? 3 : 2;
     void* a_cur = A0; void* a_nxt = Hh;
     float* s_cur = X; float* s_nxt = (float*)A0;
     void* pair_scratch = nullptr;                       // two-CTA pipeline: the h tiles cross SMs through this (L2-resident) ring
-    if (fuse_tf32 || (fuse_pairs && Co == 128)) pair_scratch = c.ws->raw(resstack_pair2_scratch_bytes());
+    if ((fuse_tf32 && tf32_impl == 2) || (fuse_pairs && Co == 128)) pair_scratch = c.ws->raw(resstack_pair2_scratch_bytes());
     int dil = 1;
     for (int i = 0; i < 8; ++i, dil *= 3) {
       snprintf(name, sizeof(name), "voc.rs%d.l%d", j, i);
@@ -598,7 +600,7 @@ int vocoder_generator(Ctx& c, const void* cond, int B, int Tc, float* wav_out, i
         pd.a = s_cur; pd.x = s_cur; pd.x_out = s_nxt; pd.dilation = dil; pd.B = B; pd.L = (int)Lout; pd.C = Co;
         pd.w1 = getw(c, p + ".c1.w", (size_t)3 * Co * Co, prec); pd.b1 = getf(c, p + ".c1.b", Co);
         pd.w2 = getw(c, p + ".c2.w", (size_t)3 * Co * Co, prec); pd.b2 = getf(c, p + ".c2.b", Co);
-        pd.write_raw = 1; pd.precision = VFX_PREC_TF32; pd.impl = 2;
+        pd.write_raw = 1; pd.precision = VFX_PREC_TF32; pd.impl = tf32_impl;
         pd.scratch = pair_scratch; pd.scratch_bytes = resstack_pair2_scratch_bytes();
         pd.stream_enc = 1; pd.stream_enc_out = i < 7 ? 1 : 0;     // the last pair hands plain x' to the final convolution
         if (!c.dry && c.rc == VFX_OK) {
@@ -607,7 +609,7 @@ int vocoder_generator(Ctx& c, const void* cond, int B, int Tc, float* wav_out, i
           snprintf(ptd, sizeof(ptd), "%s.d%d", pt, dil);
           const double els = (double)B * Lout * Co;
           ProfScope ps(c, c.e->profile > 1 ? ptd : pt, 2.0 * 2.0 * 3.0 * Co * els, 8.0 * els);
-          VFX_TRY(resstack_pair2_tc(pd, c.st));
+          VFX_TRY(tf32_impl == 3 ? resstack_pair3_tc(pd, c.st) : resstack_pair2_tc(pd, c.st));
         }
         float* t = s_cur; s_cur = s_nxt; s_nxt = t;
         continue;
@@ -749,6 +751,7 @@ int vfx_engine_create(vfx_engine** out, int device, int precision) {
   }
   vfx_engine* e = new vfx_engine();
   e->device = device; e->precision = precision;
+  if (getenv("VFX_FUSE_PAIR3")) e->fuse_pair3 = atoi(getenv("VFX_FUSE_PAIR3"));
   if (getenv("VFX_FUSE_PAIR2")) e->fuse_pair2 = atoi(getenv("VFX_FUSE_PAIR2"));      // A/B knob for bench runs
   std::vector<float> win(2048);
   std::vector<float2> tw(1024);
@@ -811,6 +814,7 @@ int vfx_engine_set_option(vfx_engine* e, const char* key, int value) {
   if (!strcmp(key, "profile")) { e->profile = value; return VFX_OK; }
   if (!strcmp(key, "fuse_pair")) { e->fuse_pair = value; return VFX_OK; }
   if (!strcmp(key, "fuse_pair2")) { e->fuse_pair2 = value; return VFX_OK; }
+  if (!strcmp(key, "fuse_pair3")) { e->fuse_pair3 = value; return VFX_OK; }
   if (!strcmp(key, "tf32_stream")) { e->tf32_stream = value; return VFX_OK; }
   set_error("set_option: unknown key '%s'", key);
   return VFX_ERR_INVALID;
@@ -1013,8 +1017,14 @@ int vfx_resstack_pair(const vfx_pair_desc* d, void* stream) {
   VFX_REQUIRE(d, "resstack_pair: null descriptor");
   const bool tf32 = d->precision == VFX_PREC_TF32;
   const bool one_cta = d->impl == 1 || (d->impl == 0 && !tf32 && d->C == 64 && !d->x_out);
-  int r = one_cta ? ((tf32 || d->x_out) ? VFX_ERR_UNSUPPORTED : resstack_pair_tc(*d, (cudaStream_t)stream))
-                  : resstack_pair2_tc(*d, (cudaStream_t)stream);
+  int r;
+  if (tf32 && (d->impl == 3 || d->impl == 0)) {            // one SM, residual stashed in TMEM; the two-CTA form on request
+    r = resstack_pair3_tc(*d, (cudaStream_t)stream);
+    if (r == VFX_ERR_UNSUPPORTED && d->impl == 0) r = resstack_pair2_tc(*d, (cudaStream_t)stream);
+  } else if (d->impl == 3) r = VFX_ERR_UNSUPPORTED;
+  else
+    r = one_cta ? ((tf32 || d->x_out) ? VFX_ERR_UNSUPPORTED : resstack_pair_tc(*d, (cudaStream_t)stream))
+                : resstack_pair2_tc(*d, (cudaStream_t)stream);
   if (r == VFX_ERR_UNSUPPORTED)
     set_error("resstack_pair: unsupported shape (bf16: C = 64 or 128; tf32: C = 64 with stream_enc; 16-byte aligned tensors)");
   return r;

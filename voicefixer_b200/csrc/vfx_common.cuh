@@ -60,13 +60,14 @@ __device__ __forceinline__ float to_f(tf32_t v) { return __uint_as_float(__float
 template <> __device__ __forceinline__ tf32_t from_f<tf32_t>(float v) { return tf32_t{round_tf32(v)}; }
 
 // Encoded tf32 stream (vfx_conv_desc.res_enc / raw_enc): S = bits(lrelu(x)) + 0x1000 -- see include/vfx_b200.h.
+// (lrelu and its inverse as max / min with the scaled value: two instructions, the same result for 0 < slope < 1)
 __device__ __forceinline__ float stream_enc(float x, float slope) {
-  const float y = x > 0.f ? x : x * slope;
+  const float y = fmaxf(x, x * slope);
   return __uint_as_float(__float_as_uint(y) + 0x1000u);
 }
 __device__ __forceinline__ float stream_dec(float s, float inv_slope) {
   const float y = __uint_as_float(__float_as_uint(s) - 0x1000u);
-  return y > 0.f ? y : y * inv_slope;
+  return fminf(y, y * inv_slope);
 }
 
 // element size of a GEMM operand / weight in the given vfx_precision
@@ -96,6 +97,7 @@ int conv_gemm_simt(int precision, const vfx_conv_desc& d, cudaStream_t st);
 int resstack_pair_tc(const vfx_pair_desc& d, cudaStream_t st);     // fused ResStack pair (bf16, C = 64), one CTA per tile
 int resstack_pair2_tc(const vfx_pair_desc& d, cudaStream_t st);    // ... two-CTA cluster pipeline (bf16 C = 128, tf32 C = 64)
 size_t resstack_pair2_scratch_bytes();
+int resstack_pair3_tc(const vfx_pair_desc& d, cudaStream_t st);    // ... tf32 C = 64 on one SM, residual stashed in TMEM
 int conv_gemm_tc(int precision, const vfx_conv_desc& d, cudaStream_t st);   // tcgen05: bf16 (kind::f16) or tf32 (kind::tf32)
 
 // y = act(scale[b][c]*x + shift[b][c]); x fp32 [B][P][C] (row pitch ldx), y operand type.
