@@ -64,8 +64,9 @@ int vfx_engine_set_tensor(vfx_engine* e, const char* name, const void* dev_ptr, 
  * "profile" (0/1/2, see vfx_profile_report; 2 = one tag per shape / dilation),
  * "fuse_pair" (BF16: width-64 ResStack pairs as one fused kernel, default 1),
  * "tf32_stream" (TF32: vocoder residual streams as one encoded tensor, vfx_conv_desc.res_enc / raw_enc, default 1),
- * "fuse_pair2" (two-CTA cluster pipeline: 1 [default] = BF16 / FP16 width-128 ResStack pairs, 2 = also TF32 width 64 [no gain],
- *  0 = off). */
+ * "fuse_pair3" (TF32: width-64 ResStack pairs as one fused kernel, residual stashed in tensor memory, default 1),
+ * "fuse_pair2" (two-CTA cluster pipeline: 1 [default] = BF16 / FP16 width-128 ResStack pairs, 2 = also TF32 width 64 when
+ *  "fuse_pair3" is 0 [no gain there], 0 = off). */
 int vfx_engine_set_option(vfx_engine* e, const char* key, int value);
 /* Number of CUDA kernels this library has launched in this process (bench.py's gpu_launches). */
 unsigned long long vfx_launch_count(void);
@@ -174,11 +175,12 @@ int vfx_conv_gemm(int precision, int impl, const vfx_conv_desc* d, void* stream)
 /* Fused ResStack pair on tcgen05:
  *   x' = x + conv2_{k3,d=1}( lrelu_0.01( conv1_{k3,dilation}( a ) + b1 ) ) + b2
  * ResStack.forward voicefixer/vocoder/model/modules.py:592-595 (layers :550-576).  The intermediate never leaves the chip.
- * Two implementations (impl: 0 = pick, 1 = one CTA per tile, 2 = two-CTA cluster pipeline: conv1 on one SM, conv2 on its
- * neighbour, the intermediate crossing through an L2-resident scratch ring):
+ * Three implementations (impl: 0 = pick, 1 = one CTA per tile [16-bit operands], 2 = two-CTA cluster pipeline: conv1 on one SM,
+ * conv2 on its neighbour, the intermediate crossing through an L2-resident scratch ring, 3 = one CTA per tile in tf32: the
+ * residual rides in the operand boxes and is stashed in tensor memory, 8 bytes of HBM traffic per element):
  *   VFX_PREC_BF16 / VFX_PREC_FP16, C = 64 (impl 1), C = 128 (impl 2): a = lrelu_0.01(x) in the operand format [B][L][C]; x fp32 is read as the residual
  *     and, if write_raw, overwritten with x' (or written to x_out); out_act (optional, bf16, must not alias a) receives act(x').
- *   VFX_PREC_TF32, C = 64 (impl 2), stream_enc = 1: a == x == the encoded stream S (vfx_conv_desc.raw_enc), fp32 [B][L][C];
+ *   VFX_PREC_TF32, C = 64 (impl 3, or 2), stream_enc = 1: a == x == the encoded stream S (vfx_conv_desc.raw_enc), fp32 [B][L][C];
  *     the result goes to x_out (required, aliasing neither input) as S' (stream_enc_out = 1) or as plain x' (0).
  * w1 / w2: [3][C][C] in the operand format, tap-major.  Other shapes return VFX_ERR_UNSUPPORTED. */
 typedef struct vfx_pair_desc {

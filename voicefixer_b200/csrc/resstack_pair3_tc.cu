@@ -15,17 +15,22 @@
 //
 //   HBM traffic per element of the pair: S in 4 B + S' out 4 B = 8 B = SURVEY 8d's algorithmic figure (two launches: 20 B).
 //
-// Roles (persistent CTA per SM, 576 threads):
+// Roles (persistent CTA per SM, 448 threads):
 //     warp 0       TMA producer: ring of operand slots, one slot = one 128-byte K chunk (32 channels) of one box
-//                    d <= 9: two halo boxes of 128 + 2d rows per tile (taps = row-shifted descriptor views);
+//                    d <= 27: two halo boxes of 128 + 2d rows per tile (taps = row-shifted descriptor views);
 //                    else:   six 128-row boxes per tile (tap 1 first -- it carries the residual --, then taps 0 and 2)
 //     warp 1       MMA issuer, software-pipelined: conv1(i), then conv2(i-1) on the h tile epilogue 1 produced meanwhile
 //     warps 2-5    epilogue 1: conv1 accumulator -> +b1 -> lrelu -> round to tf32 -> h tile (SWIZZLE_128B, two K chunks)
-//     warps 6-13   epilogue 2: accumulator + b2 + decoded residual -> S' (or plain x' for the last pair), TMA stores; two
-//                  warps per TMEM lane quarter, one 32-column half each (with four warps doing both halves through one
-//                  staging buffer this role set the pace: 1.69 ms per pair)
-//     warps 14-17  residual stash: shared memory -> TMEM, then the slot's second "empty" arrival
+//     warps 6-9    epilogue 2: accumulator + b2 + decoded residual -> S' (or plain x' for the last pair), TMA stores
+//     warps 10-13  residual stash: shared memory -> TMEM, then the slot's second "empty" arrival
 //   TMEM (512 columns): conv1 accumulator x2 | conv2 accumulator x2 | residual stash x4.
+// MEASURED (B200, B = 32 x 443 646 positions, tools/bench_pair.py --prec tf32 --impl 3): 1.55-1.60 ms per pair with halo boxes
+// (d <= 27), 1.9-2.3 ms with aligned boxes (three times the TMA bytes into shared memory; run-to-run spread with the buffer
+// addresses), against 2.93 / 3.26 ms for the two launches; DRAM traffic 7.22 GB per pair = the 8 B-per-element figure
+// (profiles/r02_pair3_tf32.txt).  What paces it is shared-memory bandwidth: an N = 64 tf32 MMA fetches 6 KB of operands per
+// 32 cycles, so the 48 MMAs of a tile plus TMA writes, the h tile, the stash read and the store staging keep the 128 B/cycle
+// port busy for ~3 600 of the tile's ~4 000 cycles (tensor pipe 36 % active).  Tried without gain: eight warps for either
+// epilogue, an L2 prefetch (cp.async.bulk.prefetch.tensor) of the tiles ahead.
 // Tiling (126 outputs per 128-row MMA tile, h rows outside [0, L) zeroed, 30-row store boxes for the last quarter) is that of
 // resstack_pair_tc.cu.  The output goes to a different buffer than the input (neighbouring tiles read S with a halo).
 #include <stdlib.h>
@@ -94,7 +99,7 @@ resstack_pair3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* const smem = smem_raw;
   if ((smem_u32(smem_raw) & 1023u) != 0u) __trap();
-  // [W1 | W2 | h (2 K chunks) | operand ring | epilogue-2 staging (8 x 4 KB) | bias1 bias2 | barriers]
+  // [W1 | W2 | h (2 K chunks) | operand ring | epilogue-2 staging (4 KB per warp) | bias1 bias2 | barriers]
   uint8_t* const w1s = smem;
   uint8_t* const w2s = smem + R_WBYTES;
   uint8_t* const hs = smem + 2 * R_WBYTES;
@@ -165,6 +170,7 @@ resstack_pair3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     for (uint32_t i = 0; i < n_my; ++i) {
       const int p0 = it.p0(), b = it.b;
       it.next(p);
+
 #pragma unroll 1
       for (int q = 0; q < nbox; ++q) {
         // per-tap order: tap 1 (k0, k1), tap 0 (k0, k1), tap 2 (k0, k1)
@@ -451,9 +457,10 @@ int resstack_pair3_tc(const vfx_pair_desc& d, cudaStream_t st) {
   p.halo = (d.dilation <= halo_max && d.dilation <= 64) ? 1u : 0u;      // a TMA box is at most 256 rows
   p.halo_rows = 128u + 2u * (uint32_t)d.dilation;
   p.slot_bytes = p.halo ? (p.halo_rows * 128u + 1023u) / 1024u * 1024u : 128u * 128u;
-  // role split (VFX_PAIR3_CFG): 0 = 4 + 4 epilogue warps, 1 = 8 warps for epilogue 1, 2 = 8 warps for epilogue 2
-  static const int cfg = getenv("VFX_PAIR3_CFG") ? atoi(getenv("VFX_PAIR3_CFG")) : 0;
-  const uint32_t e1w = cfg == 1 ? 8u : 4u, e2w = cfg == 2 ? 8u : 4u;
+  // Role split: 4 + 4 epilogue warps.  Measured alternatives (B200, B = 32, d = 3 / 243): 8 warps for epilogue 1: 1.54 / 2.15 ms,
+  // 8 warps for epilogue 2 (32 KB of staging, one ring slot less): 1.60 / 2.21 ms, against 1.55 / 1.91 ms -- the kernel is
+  // paced by shared-memory bandwidth (N = 64 MMAs fetch 6 KB of operands per 32 cycles), not by a single role.
+  constexpr uint32_t e1w = 4u, e2w = 4u;
   const uint32_t fixed = 2u * R_WBYTES + 2u * R_HPANEL + e2w * 4096u + 2u * RC * 4u + 512u /*barriers*/;
   const uint32_t budget = 227u * 1024u;
   uint32_t slots = (budget - fixed) / p.slot_bytes;
@@ -500,16 +507,11 @@ int resstack_pair3_tc(const vfx_pair_desc& d, cudaStream_t st) {
   else {
     VFX_CUDA_CHECK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
     VFX_CUDA_CHECK(cudaFuncSetAttribute(resstack_pair3_kernel<4, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    VFX_CUDA_CHECK(cudaFuncSetAttribute(resstack_pair3_kernel<8, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    VFX_CUDA_CHECK(cudaFuncSetAttribute(resstack_pair3_kernel<4, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     if (dev < 64) sms_of[dev] = num_sms;
   }
   const int grid = (int)(p.total_tiles < (uint32_t)num_sms ? p.total_tiles : (uint32_t)num_sms);
   p.d_it = grid % p.n_t; p.d_b = grid / p.n_t;
-  const int threads = (int)(6u + e1w + e2w) * 32;
-  if (e1w == 8) resstack_pair3_kernel<8, 4><<<grid, threads, smem_bytes, st>>>(tmA, tmW1, tmW2, tmO, tmO30, p);
-  else if (e2w == 8) resstack_pair3_kernel<4, 8><<<grid, threads, smem_bytes, st>>>(tmA, tmW1, tmW2, tmO, tmO30, p);
-  else resstack_pair3_kernel<4, 4><<<grid, threads, smem_bytes, st>>>(tmA, tmW1, tmW2, tmO, tmO30, p);
+  resstack_pair3_kernel<4, 4><<<grid, (int)(6u + e1w + e2w) * 32, smem_bytes, st>>>(tmA, tmW1, tmW2, tmO, tmO30, p);
   VFX_LAUNCH_CHECK();
   return VFX_OK;
 }
