@@ -329,7 +329,8 @@ def roofline_from(rep, B, L_by_stack, precision, peaks, peaks_src, tot_ms):
             flops, model_bytes = fused["flops"] / fused["count"], fused["bytes"] / fused["count"]
         elif c1 and c2:
             ms_pair, n = (c1["ms"] + c2["ms"]) / c2["count"], c2["count"]
-            kern = f"conv_gemm_tc_kernel x2 [voc.rs{j}.c1 + voc.rs{j}.c2]"
+            kern = (f"conv_ts_kernel (weights in TMEM) + conv_gemm_tc_kernel for large dilations [voc.rs{j}.c1 + voc.rs{j}.c2]"
+                    if precision == "tf32" and C == 128 else f"conv_gemm_tc_kernel x2 [voc.rs{j}.c1 + voc.rs{j}.c2]")
             flops = (c1["flops"] + c2["flops"]) / c2["count"]
             model_bytes = (c1["bytes"] + c2["bytes"]) / c2["count"]
         else:

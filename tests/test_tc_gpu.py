@@ -187,3 +187,53 @@ def test_tf32_encoded_stream(C, L, dil, impl):
     # and as the next operand it is exactly round-to-nearest(lrelu(result))
     got_op = (raw[:, 0].contiguous().view(torch.int32) & ~0x1FFF).view(torch.float32)
     assert rel_rms(got_op.cpu(), F.leaky_relu(ref, 0.01).cpu()) < 5e-4
+
+
+# ---------------------------------------------------------------------------- tf32, width 128: weights resident in TMEM
+@pytest.mark.parametrize("mode", ["act", "enc", "xsinx", "plain"])
+@pytest.mark.parametrize("L,dil,B", [(1000, 1, 2), (64, 3, 1), (63, 1, 1), (777, 9, 2), (5000, 27, 1), (3000, 81, 2),
+                                     (9000, 2187, 1), (20000, 243, 3), (130, 729, 1)])
+def test_tf32_c128_weights_in_tmem(L, dil, B, mode):
+    """conv_ts_tc.cu (the C = 128 ResStack convolutions of the tf32 mode): transposed GEMM, weights as the A operand from
+    tensor memory, activations as B.  The four output forms the vocoder uses: activated operand only (conv1), encoded residual
+    in / encoded stream out in place (conv2), encoded residual in / x + sin x operand out (last conv2 of a stack), plain
+    residual / plain raw.  Against torch on the same tf32-rounded operands (fp32 accumulation: only the order differs)."""
+    from gpu_util import conv_gemm
+    from voicefixer_b200.weights import round_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    C = 128
+    x = _rnd(B, L, C, seed=51)
+    w, wf = _op(_rnd(C, C, 3, seed=52, scale=0.08), "tf32")
+    b = _rnd(C, seed=53, scale=0.1)
+    wp = w.permute(2, 0, 1).contiguous()
+    taps = [(0, -dil), (0, 0), (0, dil)]
+    if mode == "act":           # S stream in as the operand (un-rounded bits: the tensor core truncates), lrelu operand out
+        S = _enc(x)
+        a_ref = round_tf32(F.leaky_relu(x, 0.01).cpu()).to(DEV)
+        ref = F.leaky_relu(F.conv1d(a_ref.permute(0, 2, 1), wf, b, dilation=dil, padding=dil), 0.01).permute(0, 2, 1)
+        _, act = conv_gemm(S[:, None].contiguous(), wp, taps, bias=b, want_raw=False, want_act=True, act="lrelu",
+                           act_param=0.01, precision="tf32", impl=1)
+        assert rel_rms(act[:, 0].cpu(), ref.cpu()) < ACT_TOL["tf32"]
+        assert int((act.view(torch.int32) & 0x1FFF).abs().max()) == 0
+        return
+    h, hf = _op(_rnd(B, L, C, seed=54), "tf32")                 # conv2's operand: the rounded intermediate
+    conv = F.conv1d(hf.permute(0, 2, 1), wf, b, dilation=dil, padding=dil).permute(0, 2, 1)
+    ref = x + conv
+    a = h[:, None].contiguous()
+    if mode == "enc":
+        buf = _enc(x)[:, None].contiguous()
+        raw, _ = conv_gemm(a, wp, taps, bias=b, residual=buf, out_raw=buf, res_enc=1, raw_enc=1, enc_slope=0.01,
+                           precision="tf32", impl=1)
+        assert rel_rms((_dec(raw[:, 0]) - x).cpu(), conv.cpu()) < 1e-4
+    elif mode == "xsinx":
+        buf = _enc(x)[:, None].contiguous()
+        _, act = conv_gemm(a, wp, taps, bias=b, residual=buf, want_raw=False, want_act=True, act="lrelu_xsinx", act_param=0.2,
+                           res_enc=1, enc_slope=0.01, precision="tf32", impl=1)
+        u = F.leaky_relu(ref, 0.2)
+        assert rel_rms(act[:, 0].cpu(), (u + torch.sin(u)).cpu()) < ACT_TOL["tf32"]
+        assert torch.equal(buf[:, 0], _enc(x))                   # the residual stream is untouched
+    else:
+        res = x[:, None].contiguous()
+        raw, _ = conv_gemm(a, wp, taps, bias=b, residual=res, precision="tf32", impl=1)
+        assert rel_rms((raw[:, 0] - x).cpu(), conv.cpu()) < 2e-5

@@ -7,7 +7,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libvfx_b200.so")
-SOURCES = ["engine.cu", "conv_gemm_simt.cu", "conv_gemm_tc.cu", "resstack_pair_tc.cu", "resstack_pair2_tc.cu", "resstack_pair3_tc.cu", "elementwise.cu", "frontend.cu",
+SOURCES = ["engine.cu", "conv_gemm_simt.cu", "conv_gemm_tc.cu", "conv_ts_tc.cu", "resstack_pair_tc.cu", "resstack_pair2_tc.cu", "resstack_pair3_tc.cu", "elementwise.cu", "frontend.cu",
            "gru.cu", "hf_cut.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]

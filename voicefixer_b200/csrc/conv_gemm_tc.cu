@@ -651,10 +651,17 @@ int ilog2(int v) { int l = 0; while ((1 << l) < v) ++l; return l; }
 
 }  // namespace
 
+// conv_ts_tc.cu: tf32, k = 3, 128 -> 128 channels with the weights resident in tensor memory; VFX_ERR_UNSUPPORTED for anything else
+int conv_ts_tc(const vfx_conv_desc& d, cudaStream_t st);
+
 int conv_gemm_tc(int precision, const vfx_conv_desc& d, cudaStream_t st) {
   // ---- shapes this kernel covers; everything else returns UNSUPPORTED (caller uses the SIMT kernel)
   if (precision != VFX_PREC_BF16 && precision != VFX_PREC_TF32 && precision != VFX_PREC_FP16) return VFX_ERR_UNSUPPORTED;
   const bool tf32 = precision == VFX_PREC_TF32, fp16 = precision == VFX_PREC_FP16;
+  if (tf32) {                                    // width-128 k3 convolutions: weights resident in tensor memory (conv_ts_tc.cu)
+    const int r = conv_ts_tc(d, st);
+    if (r != VFX_ERR_UNSUPPORTED) return r;
+  }
   const int esz = tf32 ? 4 : 2;
   int KC = 0;
   if (tf32) { if (d.Cin % 32 == 0) KC = 32; }
