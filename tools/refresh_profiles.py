@@ -5,10 +5,11 @@ import collections, csv, io, os, re, shutil, subprocess, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 os.chdir(ROOT)
 head = subprocess.run(["git", "rev-parse", "--short", "HEAD"], capture_output=True, text=True).stdout.strip()
-for n in ("pair_c64", "pair2_c128", "rs2", "unet_c32", "gru", "voc_post", "rs3_tf32", "pair3_tf32"):
+INCR = len(sys.argv) > 1 and sys.argv[1] == "b"      # only what tools/capture_r02b.sh brought back (conv_ts kernel + tf32 launch list)
+for n in (("ts_c128_tf32",) if INCR else ("pair_c64", "pair2_c128", "rs2", "unet_c32", "gru", "voc_post", "rs3_tf32", "pair3_tf32")):
     subprocess.run([sys.executable, "tools/ncu_summary.py", f"gpurun_out/r02_{n}.ncu-rep", f"profiles/r02_{n}.txt",
                     f"round 2, captured from the sources of commit {head}, B=32 (tools/capture_r02.sh)"], capture_output=True)
-for P in ("bf16", "tf32"):
+for P in (("tf32",) if INCR else ("bf16", "tf32")):
     rows = list(csv.reader(open(f"gpurun_out/r02_launches_{P}.csv")))
     hi = [i for i, r in enumerate(rows) if r and r[0] == "ID"][0]
     hdr, data = rows[hi], rows[hi + 2:]
@@ -27,6 +28,8 @@ for P in ("bf16", "tf32"):
         out.write(f"{k},{c},{ms:.3f},{ms / tot:.4f}\n")
     open(f"profiles/r02_launch_list_summary_{P}.csv", "w").write(out.getvalue())
     shutil.copy(f"gpurun_out/r02_launches_{P}.csv", f"profiles/r02_launch_list_{P}.csv")
+if INCR:
+    sys.exit(0)
 if os.path.exists("profiles/ncu_traffic.json"):
     os.remove("profiles/ncu_traffic.json")
 subprocess.run([sys.executable, "tools/update_traffic.py", "gpurun_out/r02_pair_c64.ncu-rep", "bf16:voc.rs3.pair:B32", "1",
